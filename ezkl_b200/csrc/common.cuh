@@ -1,0 +1,81 @@
+// common.cuh — error plumbing, device scratch arena and block-level helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace b200 {
+
+// Thread-local last-error string behind b200_last_error() (include/ezkl_b200.h).
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define B200_CUDA(call)                                                                                  \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            ::b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));     \
+            return -2;                                                                                   \
+        }                                                                                                \
+    } while (0)
+
+#define B200_CHECK(cond, code, ...)                                                                      \
+    do {                                                                                                 \
+        if (!(cond)) { ::b200::set_error(__VA_ARGS__); return (code); }                                  \
+    } while (0)
+
+// Growable device scratch buffer (one per call-site purpose per context); never shrinks.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return -2; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+#if defined(__CUDACC__)
+// Exclusive scan of one uint32 per thread across the block (blockDim.x <= 1024, multiple of 32).
+// Returns the exclusive prefix; *total gets the block sum (valid in every thread).
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t block_total;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < nw ? warp_sums[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (unsigned)d) wi += t;
+        }
+        if (lane < nw) warp_sums[lane] = wi - w;
+        if (lane == 31) block_total = wi;
+    }
+    __syncthreads();
+    uint32_t r = warp_sums[wid] + incl - v;
+    *total = block_total;
+    __syncthreads();
+    return r;
+}
+#endif
+
+}  // namespace b200

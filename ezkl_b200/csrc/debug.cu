@@ -1,0 +1,110 @@
+// debug.cu — small self-test entry points (b200_debug_*) used only by tests/ to localise a failure to one layer
+// (field arithmetic, group law, digit recoding) before the composite kernels are blamed.  Not part of the drop-in ABI.
+#include "../../include/ezkl_b200.h"
+#include "msm.cuh"
+
+namespace b200 {
+template <class Tag>
+__global__ void k_dbg_field(int op, const Fp<Tag>* a, const Fp<Tag>* b, Fp<Tag>* o, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<Tag> x = fp_load(a + i), y = fp_load(b + i), r;
+    if (op == 0) r = x + y; else if (op == 1) r = x - y; else if (op == 2) r = x * y; else if (op == 3) r = fp_inv(x); else r = fp_from_mont(x);
+    fp_store(o + i, r);
+}
+// op 0: affine a + affine b; 1: 2*a; 2: k*a (k = b.x.l[0] as small integer); 3: a + a via add_mixed (doubling branch); 4: a + (-a)
+__global__ void k_dbg_g1(int op, const G1Affine* a, const G1Affine* b, G1Affine* o, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = a[i], q = b[i];
+    G1Xyzz r;
+    if (op == 0) r = g1_add_mixed(g1_to_xyzz(p), q);
+    else if (op == 1) r = g1_dbl(g1_to_xyzz(p));
+    else if (op == 2) r = g1_mul_small(g1_to_xyzz(p), q.x.l[0]);
+    else if (op == 3) r = g1_add(g1_to_xyzz(p), g1_dbl_affine(q));
+    else r = g1_add_mixed(g1_to_xyzz(p), g1_neg(p));
+    o[i] = g1_to_affine(r);
+}
+__global__ void k_dbg_digits(const Fr* s, int c, int W, int32_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = fp_from_mont(fp_load(s + i));
+    uint32_t carry = 0;
+    for (int w = 0; w < W; ++w) out[i * W + w] = msm_next_digit(v.l, c, &carry);
+}
+}  // namespace b200
+using namespace b200;
+
+#pragma GCC visibility push(default)
+extern "C" {
+// all pointers are HOST pointers; the call stages, runs one kernel and copies back
+int b200_debug_field_op(int field, int op, const b200_fr* a, const b200_fr* b, b200_fr* out, size_t n) {
+    void *da, *db, *dout;
+    B200_CUDA(cudaMalloc(&da, 32 * n)); B200_CUDA(cudaMalloc(&db, 32 * n)); B200_CUDA(cudaMalloc(&dout, 32 * n));
+    B200_CUDA(cudaMemcpy(da, a, 32 * n, cudaMemcpyHostToDevice)); B200_CUDA(cudaMemcpy(db, b, 32 * n, cudaMemcpyHostToDevice));
+    if (field == 0) k_dbg_field<FrTag><<<div_up(n, 128), 128>>>(op, (const Fr*)da, (const Fr*)db, (Fr*)dout, n);
+    else k_dbg_field<FqTag><<<div_up(n, 128), 128>>>(op, (const Fq*)da, (const Fq*)db, (Fq*)dout, n);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpy(out, dout, 32 * n, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return 0;
+}
+int b200_debug_g1_op(int op, const b200_g1_affine* a, const b200_g1_affine* b, b200_g1_affine* out, size_t n) {
+    void *da, *db, *dout;
+    B200_CUDA(cudaMalloc(&da, 64 * n)); B200_CUDA(cudaMalloc(&db, 64 * n)); B200_CUDA(cudaMalloc(&dout, 64 * n));
+    B200_CUDA(cudaMemcpy(da, a, 64 * n, cudaMemcpyHostToDevice)); B200_CUDA(cudaMemcpy(db, b, 64 * n, cudaMemcpyHostToDevice));
+    k_dbg_g1<<<div_up(n, 64), 64>>>(op, (const G1Affine*)da, (const G1Affine*)db, (G1Affine*)dout, n);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpy(out, dout, 64 * n, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return 0;
+}
+int b200_debug_digits(const b200_fr* s, size_t n, int c, int32_t* out /* n * ceil(255/c) */) {
+    const int W = (255 + c - 1) / c;
+    void *ds, *dout;
+    B200_CUDA(cudaMalloc(&ds, 32 * n)); B200_CUDA(cudaMalloc(&dout, 4 * n * W));
+    B200_CUDA(cudaMemcpy(ds, s, 32 * n, cudaMemcpyHostToDevice));
+    k_dbg_digits<<<div_up(n, 128), 128>>>((const Fr*)ds, c, W, (int32_t*)dout, n);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpy(out, dout, 4 * n * W, cudaMemcpyDeviceToHost));
+    cudaFree(ds); cudaFree(dout);
+    return 0;
+}
+// host-only: the same recoding routine compiled for the CPU (lets the not-gpu tests check it without a device)
+int b200_debug_digits_host(const b200_fr* s_canonical, size_t n, int c, int32_t* out) {
+    const int W = (255 + c - 1) / c;
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t v[8]; memcpy(v, &s_canonical[i], 32);
+        uint32_t carry = 0;
+        for (int w = 0; w < W; ++w) out[i * W + w] = msm_next_digit(v, c, &carry);
+    }
+    return 0;
+}
+// host-only: group law / field code compiled for the CPU through the portable path (not-gpu tests)
+int b200_debug_host_g1_op(int op, const b200_g1_affine* a, const b200_g1_affine* b, b200_g1_affine* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        G1Affine p, q; memcpy(&p, &a[i], 64); memcpy(&q, &b[i], 64);
+        G1Xyzz r;
+        if (op == 0) r = g1_add_mixed(g1_to_xyzz(p), q);
+        else if (op == 1) r = g1_dbl(g1_to_xyzz(p));
+        else if (op == 2) r = g1_mul_small(g1_to_xyzz(p), q.x.l[0]);
+        else if (op == 3) r = g1_add(g1_to_xyzz(p), g1_dbl_affine(q));
+        else r = g1_add_mixed(g1_to_xyzz(p), g1_neg(p));
+        G1Affine o = g1_to_affine(r); memcpy(&out[i], &o, 64);
+    }
+    return 0;
+}
+int b200_debug_host_field_op(int field, int op, const b200_fr* a, const b200_fr* b, b200_fr* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (field == 0) { Fr x, y, r; memcpy(&x, &a[i], 32); memcpy(&y, &b[i], 32);
+            if (op == 0) r = x + y; else if (op == 1) r = x - y; else if (op == 2) r = x * y; else if (op == 3) r = fp_inv(x); else r = fp_from_mont(x);
+            memcpy(&out[i], &r, 32);
+        } else { Fq x, y, r; memcpy(&x, &a[i], 32); memcpy(&y, &b[i], 32);
+            if (op == 0) r = x + y; else if (op == 1) r = x - y; else if (op == 2) r = x * y; else if (op == 3) r = fp_inv(x); else r = fp_from_mont(x);
+            memcpy(&out[i], &r, 32);
+        }
+    }
+    return 0;
+}
+}
+#pragma GCC visibility pop

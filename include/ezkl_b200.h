@@ -1,0 +1,118 @@
+/*
+ * ezkl_b200.h — C ABI of libezkl_b200.so, the Blackwell (sm_100a) proving backend for ezkl's Halo2/KZG prover.
+ *
+ * This is the drop-in boundary: the entry points a Rust `mod b200;` inside the halo2 fork binds in place
+ * of `mod icicle;` behind cfg(feature = "gpu-accelerated") (/root/reference/Cargo.toml:259), so that
+ * `pfsys::create_proof_circuit` / `create_keys` (/root/reference/src/pfsys/mod.rs:404-489, 376-400), `ezkl prove`
+ * (/root/reference/src/execute.rs:1575-1627) and the Python bindings stay unchanged.  INTEGRATION.md shows the shim.
+ *
+ * Conventions
+ *   - return 0 = ok, < 0 = error (-1 bad argument, -2 CUDA failure, -3 not initialised); message via b200_last_error()
+ *     (thread-local).  Nothing throws or aborts across the boundary; there is NO CPU fallback — without a usable
+ *     sm_100 device every compute entry point fails with -2/-3.
+ *   - the caller owns every host pointer for the duration of the call only; the library never frees caller memory.
+ *   - Fr / Fq: 4 x u64 little-endian limbs in Montgomery form, exactly halo2curves' in-memory representation
+ *     (zero-copy from &[Fr]).  G1 affine = {x, y} 64 B, identity = (0,0).  G1 Jacobian = {x, y, z} 96 B, identity z = 0.
+ *   - every call is synchronous with respect to its host buffers and re-entrant: each calling thread gets its own CUDA
+ *     stream and scratch arena (halo2 commits / transforms columns from Rayon worker threads).
+ *   - MSM results are returned NORMALISED (z = 1, or (0,1,0) for the identity), so bytes are canonical and independent
+ *     of accumulation order: what `best_multiexp(..).to_affine()` / `batch_normalize` yields on the CPU prover.
+ *   - the *_dev entry points take device pointers (e.g. torch tensors' data_ptr) and a cudaStream_t (NULL = the
+ *     calling thread's library stream); they do not synchronise.
+ */
+#ifndef EZKL_B200_H
+#define EZKL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } b200_fr;              /* halo2curves::bn256::Fr, Montgomery */
+typedef struct { uint64_t l[4]; } b200_fq;              /* halo2curves::bn256::Fq, Montgomery */
+typedef struct { b200_fq x, y; } b200_g1_affine;        /* halo2curves::bn256::G1Affine */
+typedef struct { b200_fq x, y, z; } b200_g1_jac;        /* halo2curves::bn256::G1 */
+typedef struct { b200_fq x, y, zz, zzz; } b200_g1_xyzz; /* device-side partial sums (x = X/ZZ, y = Y/ZZZ), identity zz = 0 */
+
+/* ---- lifecycle: replaces halo2_proofs::icicle::try_load_and_set_backend_device("CUDA") + icicle_runtime::warmup
+ *      (/root/reference/src/execute.rs:85-97).  device < 0 keeps the current device (e.g. the one torch selected). */
+int b200_init(int device);
+void b200_shutdown(void);
+const char* b200_last_error(void);
+int b200_version(void);
+/* kernels launched by this library since load (all threads); used by bench.py's gpu_launches */
+uint64_t b200_launch_count(void);
+
+/* ---- SRS bases: ParamsKZG.g / .g_lagrange uploaded once (src/pfsys/srs.rs:30-47 loads them; every commit reuses them).
+ *      Registration builds the window-precomputed table on the device.  window_bits = 0 picks it from n. */
+int b200_bases_register(const b200_g1_affine* bases, size_t n, int window_bits, uint64_t* handle);
+int b200_bases_register_dev(const void* d_bases, size_t n, int window_bits, uint64_t* handle);
+int b200_bases_release(uint64_t handle);
+int b200_bases_info(uint64_t handle, size_t* n, int* window_bits, int* windows);
+
+/* ---- MSM: halo2_proofs::arithmetic::best_multiexp / ParamsKZG::{commit, commit_lagrange}
+ *      (in-tree caller: /root/reference/src/circuit/modules/polycommit.rs:71).  n <= registered length. */
+int b200_msm(uint64_t bases, const b200_fr* scalars, size_t n, b200_g1_jac* out);
+/* batch columns sharing the bases (the advice / lookup / permutation commit loops of create_proof) */
+int b200_msm_batch(uint64_t bases, const b200_fr* const* scalars, size_t n, size_t batch, b200_g1_jac* out);
+/* device-resident: scalars[b*stride + i]; writes batch un-normalised XYZZ partial sums to d_out */
+int b200_msm_batch_dev(uint64_t bases, const void* d_scalars, size_t n, size_t stride, size_t batch, void* d_out_xyzz, void* stream);
+/* out[g] = sum_{j < count} points[g*count + j] (device XYZZ arrays): the local add after an all-gather of per-rank partials */
+int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void* d_out_xyzz, void* stream);
+/* host: XYZZ partials -> normalised Jacobian (one shared inversion) */
+int b200_g1_normalize(const b200_g1_xyzz* points, size_t n, b200_g1_jac* out);
+
+/* ---- NTT: halo2_proofs::arithmetic::best_fft and poly/domain.rs EvaluationDomain transforms -------------------- */
+/* best_fft(a, omega, log_n): natural order in/out, a[j] <- sum_i a[i] omega^(ij) */
+int b200_fft(b200_fr* a, uint32_t log_n, const b200_fr* omega);
+int b200_fft_batch(b200_fr* const* a, size_t batch, uint32_t log_n, const b200_fr* omega);
+/* EvaluationDomain::ifft(a, omega_inv, log_n, divisor): fft with omega_inv, then every element * divisor */
+int b200_ifft(b200_fr* a, uint32_t log_n, const b200_fr* omega_inv, const b200_fr* divisor);
+int b200_ifft_batch(b200_fr* const* a, size_t batch, uint32_t log_n, const b200_fr* omega_inv, const b200_fr* divisor);
+/* coeff_to_extended: out[j] = p(zeta * ext_omega^j), j < 2^ext_k; coeffs has n_coeffs <= 2^ext_k entries */
+int b200_coeff_to_extended(const b200_fr* coeffs, size_t n_coeffs, uint32_t ext_k, const b200_fr* ext_omega, const b200_fr* zeta, b200_fr* out);
+int b200_coeff_to_extended_batch(const b200_fr* const* coeffs, size_t batch, size_t n_coeffs, uint32_t ext_k, const b200_fr* ext_omega, const b200_fr* zeta, b200_fr* const* out);
+/* extended_to_coeff: ifft over the extended domain, * divisor, undo the zeta coset; caller truncates */
+int b200_extended_to_coeff(b200_fr* a, uint32_t ext_k, const b200_fr* ext_omega_inv, const b200_fr* ext_ifft_divisor, const b200_fr* zeta);
+/* device-resident generic transform: dst[p][j] = post(j) * sum_{i<n_in} pre(i) src[p][i] omega^(ij).
+ * pre/post: mode 0 none, 1 constant c[0], 3 cycle c[i mod 3]; c points to HOST constants. tmp: 2^log_n * batch scratch. */
+int b200_ntt_dev(const void* d_src, size_t src_stride, size_t n_in, void* d_tmp, void* d_dst, size_t dst_stride, uint32_t log_n,
+                 const b200_fr* omega, int pre_mode, const b200_fr* pre, int post_mode, const b200_fr* post, size_t batch, void* stream);
+
+/* ---- column polynomial ops (halo2 `parallelize` loops; create_proof stages 2-9) ---------------------------------
+ * op: 0 add, 1 sub, 2 mul (element-wise), 3 scale (out = a * s), 4 axpy (out = a + s * b).  out may alias a or b. */
+int b200_poly_op(int op, const b200_fr* a, const b200_fr* b, const b200_fr* s, b200_fr* out, size_t n);
+int b200_poly_op_dev(int op, const void* d_a, const void* d_b, const b200_fr* s, void* d_out, size_t n, void* stream);
+/* a[i] *= consts[i mod period]: distribute_powers_zeta (period 3) / divide_by_vanishing_poly (period 2^(ext_k-k)) */
+int b200_poly_scale_cycle(b200_fr* a, size_t n, const b200_fr* consts, uint32_t period);
+int b200_poly_scale_cycle_dev(void* d_a, size_t n, const b200_fr* consts, uint32_t period, void* stream);
+/* eval_polynomial(coeffs, x) */
+int b200_poly_eval(const b200_fr* coeffs, size_t n, const b200_fr* x, b200_fr* out);
+/* out[p] = polys[p](x[p]), p < batch: the evaluation round of create_proof */
+int b200_poly_eval_batch(const b200_fr* const* polys, size_t n, const b200_fr* x, size_t batch, b200_fr* out);
+int b200_poly_eval_batch_dev(const void* d_polys, size_t stride, size_t n, const b200_fr* x, size_t batch, void* d_out, void* stream);
+/* ff::BatchInvert (zeros stay zero) */
+int b200_batch_invert(b200_fr* a, size_t n);
+int b200_batch_invert_dev(void* d_a, size_t n, void* stream);
+/* out[0] = init, out[i+1] = out[i] (* or +) a[i]: permutation z(X) / mv-lookup phi(X) running columns */
+int b200_prefix_scan(int product, const b200_fr* a, size_t n, const b200_fr* init, b200_fr* out);
+int b200_prefix_scan_dev(int product, const void* d_a, size_t n, const b200_fr* init, void* d_out, void* stream);
+/* kate_division(a, b): quotient of a(X) by (X - b), n-1 coefficients */
+int b200_kate_division(const b200_fr* a, size_t n, const b200_fr* b, b200_fr* q);
+int b200_kate_division_dev(const void* d_a, size_t n, const b200_fr* b, void* d_q, void* stream);
+
+/* ---- device / pinned memory helpers for callers without their own CUDA runtime ---------------------------------- */
+int b200_dev_alloc(void** d_ptr, size_t bytes);
+int b200_dev_free(void* d_ptr);
+int b200_dev_upload(void* d_dst, const void* h_src, size_t bytes);
+int b200_dev_download(void* h_dst, const void* d_src, size_t bytes);
+int b200_host_alloc(void** h_ptr, size_t bytes);      /* pinned */
+int b200_host_free(void* h_ptr);
+int b200_sync(void);                                   /* the calling thread's library stream */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EZKL_B200_H */

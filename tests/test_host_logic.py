@@ -1,0 +1,117 @@
+"""CPU-side checks of the product: C-ABI surface, loud failure without a device, and the host-compiled (portable-path)
+field / group-law / digit-recoding code that the CUDA kernels share with the host, against the oracle."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from ezkl_b200 import _native as nat
+from ezkl_b200 import fields as F
+from oracle import oracle as orc
+from oracle import pyref
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ezkl_b200.h")).read()
+    names = re.findall(r"^\s*(?:int|void|uint64_t|const char\*)\s+(b200_\w+)\s*\(", hdr, flags=re.M)
+    assert len(names) >= 40
+    lib = nat.lib()
+    for nm in names:
+        assert hasattr(lib, nm), "libezkl_b200.so does not export %s" % nm
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a usable CUDA device the product must fail loudly (never compute on the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = nat.lib()
+    assert lib.b200_init(C.c_int(-1)) != 0
+    assert b"no CUDA device" in lib.b200_last_error()
+    a = np.zeros((4, 4), np.uint64)
+    w = np.zeros(4, np.uint64)
+    assert lib.b200_fft(nat.ptr(a), C.c_uint32(2), nat.ptr(w)) == -3
+    out = np.zeros(12, np.uint64)
+    assert lib.b200_msm(C.c_uint64(1), nat.ptr(a), C.c_size_t(4), nat.ptr(out)) == -3
+    with pytest.raises(nat.B200Error):
+        nat.init(-1)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ezkl_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in src.replace("# oracle-free", ""), "%s mentions the oracle" % fn
+
+
+def test_host_constants_match_oracle():
+    assert F.FR_MODULUS == pyref.R and F.FQ_MODULUS == pyref.P
+    assert F.FR_ROOT_OF_UNITY == pyref.FR_ROOT_OF_UNITY and F.FR_ZETA == pyref.FR_ZETA
+    assert np.array_equal(F.fr_to_limbs(1), orc.fr_one())
+    assert F.fr_from_limbs(orc.omega(17)) == pyref.omega_for(17)
+
+
+def test_portable_field_ops_vs_oracle():
+    L = nat.lib()
+    rng = random.Random(5)
+    for fid, (field, mod) in enumerate((("fr", pyref.R), ("fq", pyref.P))):
+        xs = [rng.randrange(mod) for _ in range(300)] + [0, 1, mod - 1]
+        ys = [rng.randrange(mod) for _ in range(300)] + [mod - 1, 0, mod - 1]
+        a = np.stack([H.int_to_limbs(pyref.to_mont(x, mod)) for x in xs])
+        b = np.stack([H.int_to_limbs(pyref.to_mont(y, mod)) for y in ys])
+        for opi, op in enumerate(("add", "sub", "mul")):
+            out = np.zeros_like(a)
+            assert L.b200_debug_host_field_op(fid, opi, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))) == 0
+            assert np.array_equal(out, orc.field_op(field, op, a, b)), (field, op)
+        out = np.zeros_like(a)
+        L.b200_debug_host_field_op(fid, 3, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs)))
+        assert np.array_equal(out, orc.fr_inv(a) if field == "fr" else orc.fq_inv(a))
+
+
+def test_group_law_vs_oracle_including_degenerate_inputs():
+    L = nat.lib()
+    rng = random.Random(6)
+    bases = orc.gen_bases(64, seed=9, threads=2)
+    A, B = bases[:32].copy(), bases[32:].copy()
+    A[0] = 0          # identity + P
+    B[1] = 0          # P + identity
+    A[2] = B[2]       # P + P through the mixed-add doubling branch
+    n = C.c_size_t(32)
+    out = np.zeros_like(A)
+    L.b200_debug_host_g1_op(0, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    assert np.array_equal(out, orc.g1_add_affine(A, B))
+    L.b200_debug_host_g1_op(1, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    assert np.array_equal(out, orc.g1_add_affine(A, A))
+    K = B.copy()
+    ks = [rng.randrange(1 << 20) for _ in range(32)]
+    ks[3], ks[4] = 0, 1
+    for i, k in enumerate(ks):
+        K[i, 0] = k
+    L.b200_debug_host_g1_op(2, nat.ptr(A), nat.ptr(K), nat.ptr(out), n)
+    assert np.array_equal(out, orc.g1_scalar_mul(A, H.fr_array(ks)))
+    L.b200_debug_host_g1_op(3, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    assert np.array_equal(out, orc.g1_add_affine(A, orc.g1_add_affine(B, B)))
+    out[:] = 1
+    L.b200_debug_host_g1_op(4, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    assert not out.any()      # P + (-P) = identity = (0,0)
+
+
+@pytest.mark.parametrize("c", [4, 7, 8, 13, 15, 16, 17, 20, 22, 24])
+def test_signed_window_recoding(c):
+    L = nat.lib()
+    rng = random.Random(c)
+    xs = [rng.randrange(pyref.R) for _ in range(200)] + [0, 1, pyref.R - 1, 1 << 253, (1 << c) - 1, 1 << (c - 1), (1 << (c - 1)) + 1]
+    can = np.stack([H.int_to_limbs(x) for x in xs])
+    W = (255 + c - 1) // c
+    out = np.zeros((len(xs), W), np.int32)
+    L.b200_debug_digits_host(nat.ptr(can), C.c_size_t(len(xs)), C.c_int(c), out.ctypes.data_as(C.c_void_p))
+    for i, x in enumerate(xs):
+        assert sum(int(out[i, w]) << (c * w) for w in range(W)) == x
+        assert all(-(1 << (c - 1)) <= int(d) <= (1 << (c - 1)) for d in out[i])
