@@ -79,6 +79,33 @@ static void normalize_host(const G1Xyzz* pts, size_t n, b200_g1_jac* out) {
     }
 }
 
+// ---- profiling (CUDA events on the launching stream) ------------------------------------------------------------
+static std::atomic<bool> g_prof{false};
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static thread_local std::vector<ProfRec> tl_prof_open;
+bool prof_enabled() { return g_prof.load(std::memory_order_relaxed); }
+void prof_mark(int cls, cudaStream_t st, bool begin) {
+    if (begin) {
+        ProfRec r; r.cls = cls;
+        cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        tl_prof_open.push_back(r);
+    } else {
+        for (size_t i = tl_prof_open.size(); i-- > 0;) {
+            if (tl_prof_open[i].cls == cls) {
+                ProfRec r = tl_prof_open[i];
+                tl_prof_open.erase(tl_prof_open.begin() + i);
+                cudaEventRecord(r.e1, st);
+                std::lock_guard<std::mutex> lk(g_prof_mu);
+                g_prof_recs.push_back(r);
+                break;
+            }
+        }
+    }
+}
+
 static MsmTable* find_table(uint64_t h) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_tables.find(h);
@@ -136,6 +163,24 @@ void b200_shutdown(void) {
     g_tables.clear();
     g_ntt.release();
     g_inited.store(false);
+}
+
+// ---- profiling -------------------------------------------------------------------------------------------------
+int b200_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof_recs.clear();
+    g_prof.store(on != 0);
+    return 0;
+}
+int b200_profile_read(int cls, double* total_ms, uint64_t* count) {
+    B200_CHECK(cls >= 0 && cls < PROF_NCLASS && total_ms && count, -1, "profile_read: bad argument");
+    B200_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double ms = 0; uint64_t n = 0;
+    for (auto& r : g_prof_recs) if (r.cls == cls) { float t = 0; if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms += t; ++n; } }
+    *total_ms = ms; *count = n;
+    return 0;
 }
 
 // ---- memory helpers ---------------------------------------------------------------------------------------
@@ -248,6 +293,13 @@ int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void
     B200_CHECK(d_points_xyzz && d_out_xyzz, -1, "g1_sum: null pointer");
     int rc = g1_sum_run(reinterpret_cast<const G1Xyzz*>(d_points_xyzz), groups, count, reinterpret_cast<G1Xyzz*>(d_out_xyzz), pick_stream(c, stream));
     if (!rc) g_launches += 1;
+    return rc;
+}
+int b200_g1_generate_dev(uint64_t seed, size_t n, void* d_out_affine, void* stream) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(d_out_affine, -1, "g1_generate: null pointer");
+    int rc = g1_generate_run(seed, n, reinterpret_cast<G1Affine*>(d_out_affine), pick_stream(c, stream));
+    if (!rc && n) g_launches += 1;
     return rc;
 }
 int b200_g1_normalize(const b200_g1_xyzz* points, size_t n, b200_g1_jac* out) {

@@ -43,6 +43,16 @@ struct DevBuf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Optional device-side timing of kernel classes with CUDA events on the launching stream (bench.py's roofline leg).
+enum ProfClass { PROF_MSM_ACCUMULATE = 0, PROF_MSM_TOTAL = 1, PROF_NTT = 2, PROF_POLY = 3, PROF_NCLASS = 4 };
+bool prof_enabled();
+void prof_mark(int cls, cudaStream_t st, bool begin);
+struct ProfScope {
+    int cls; cudaStream_t st; bool on;
+    ProfScope(int c, cudaStream_t s) : cls(c), st(s), on(prof_enabled()) { if (on) prof_mark(cls, st, true); }
+    ~ProfScope() { if (on) prof_mark(cls, st, false); }
+};
+
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 #if defined(__CUDACC__)

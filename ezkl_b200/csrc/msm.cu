@@ -310,6 +310,35 @@ __global__ void __launch_bounds__(TREE_THREADS) k_final(const G1Xyzz* __restrict
     if (threadIdx.x == 0) out[col] = acc;
 }
 
+// synthetic distinct bases for benchmarks / tests: out[i] = [h(seed, i)] * G, affine (G = (1, 2))
+__global__ void __launch_bounds__(128) k_g1_generate(uint64_t seed, size_t n, G1Affine* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    uint64_t z = seed + 0x9e3779b97f4a7c15ull * (uint64_t)(i + 1);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        z += 0x9e3779b97f4a7c15ull;
+        uint64_t x = z; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull; x ^= x >> 31;
+        s[2 * w] = (uint32_t)x; s[2 * w + 1] = (uint32_t)(x >> 32);
+    }
+    s[7] &= 0x0fffffffu;        // < 2^252 < r
+    G1Affine g; g.x = fp_one<FqTag>(); g.y = fp_one<FqTag>() + fp_one<FqTag>();
+    G1Xyzz acc = g1_xyzz_identity();
+#pragma unroll 1
+    for (int b = 251; b >= 0; --b) {
+        acc = g1_dbl(acc);
+        if ((s[b >> 5] >> (b & 31)) & 1) acc = g1_add_mixed(acc, g);
+    }
+    out[i] = g1_to_affine(acc);
+}
+int g1_generate_run(uint64_t seed, size_t n, G1Affine* d_out, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_g1_generate<<<div_up(n, 128), 128, 0, st>>>(seed, n, d_out);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int g1_sum_run(const G1Xyzz* d_points, size_t groups, size_t count, G1Xyzz* d_out, cudaStream_t st) {
     if (groups == 0) return 0;
     B200_CHECK(groups <= 0x7fffffffu && count <= 0xffffffffu, -1, "g1_sum: sizes out of range");
@@ -376,6 +405,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     G1Xyzz* bucket_sums = chunk_sums + (size_t)batch * chunk_stride;
     G1Xyzz* partials = bucket_sums + (size_t)batch * nb;
 
+    ProfScope ps_total(PROF_MSM_TOTAL, st);
     B200_CUDA(cudaMemsetAsync(hist, 0, counts_words * 4, st));
     const unsigned dig_blocks = min(div_up(n, 256), 148u * 8u);
     dim3 gd(dig_blocks, batch);
@@ -387,7 +417,10 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const unsigned ch_blocks = min(div_up(chunk_stride, 256), 148u * 8u);
     k_order_chunks<<<dim3(ch_blocks, batch), 256, 0, st>>>(chunk_len, chunk_stride, chunk_offs, nb, len_offs, len_cursor, cap, order);
     const unsigned acc_blocks = min(div_up(chunk_stride, 128), 148u * 16u);
-    k_accumulate<<<dim3(acc_blocks, batch), 128, 0, st>>>(t.d_table, ents, ent_stride, chunk_start, chunk_len, order, chunk_stride, chunk_offs, nb, chunk_sums);
+    {
+        ProfScope ps(PROF_MSM_ACCUMULATE, st);
+        k_accumulate<<<dim3(acc_blocks, batch), 128, 0, st>>>(t.d_table, ents, ent_stride, chunk_start, chunk_len, order, chunk_stride, chunk_offs, nb, chunk_sums);
+    }
     k_combine<<<dim3(div_up(nb, 128), batch), 128, 0, st>>>(chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     k_combine_heavy<<<dim3(32, batch), TREE_THREADS, 0, st>>>(heavy, heavy_stride, chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     k_reduce<<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts);

@@ -185,6 +185,7 @@ int ntt_run(NttContext& ctx, const Fr* d_src, size_t src_stride, size_t n_in, Fr
     B200_CHECK(n_in <= N, -1, "ntt: n_in %zu > N", n_in);
     NttPlan* p = ctx.get(log_n, omega, st);
     if (!p) return -2;
+    ProfScope ps(PROF_NTT, st);
     PassArgs a;
     memset(&a, 0, sizeof a);
     a.pre = pre; a.post = post;

@@ -45,6 +45,12 @@ int b200_version(void);
 /* kernels launched by this library since load (all threads); used by bench.py's gpu_launches */
 uint64_t b200_launch_count(void);
 
+/* device-side timing of kernel classes with CUDA events on the launching stream (off by default).
+ * cls: 0 = MSM bucket-accumulation kernel, 1 = whole MSM pipeline, 2 = NTT (all passes of a call), 3 = poly.
+ * b200_profile_enable(1) clears earlier records; b200_profile_read synchronises the device and sums the class. */
+int b200_profile_enable(int on);
+int b200_profile_read(int cls, double* total_ms, uint64_t* count);
+
 /* ---- SRS bases: ParamsKZG.g / .g_lagrange uploaded once (src/pfsys/srs.rs:30-47 loads them; every commit reuses them).
  *      Registration builds the window-precomputed table on the device.  window_bits = 0 picks it from n. */
 int b200_bases_register(const b200_g1_affine* bases, size_t n, int window_bits, uint64_t* handle);
@@ -61,6 +67,8 @@ int b200_msm_batch(uint64_t bases, const b200_fr* const* scalars, size_t n, size
 int b200_msm_batch_dev(uint64_t bases, const void* d_scalars, size_t n, size_t stride, size_t batch, void* d_out_xyzz, void* stream);
 /* out[g] = sum_{j < count} points[g*count + j] (device XYZZ arrays): the local add after an all-gather of per-rank partials */
 int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void* d_out_xyzz, void* stream);
+/* synthetic SRS-shaped bases for benchmarks: out[i] = [splitmix(seed, i)] * G, affine, pairwise distinct w.h.p. */
+int b200_g1_generate_dev(uint64_t seed, size_t n, void* d_out_affine, void* stream);
 /* host: XYZZ partials -> normalised Jacobian (one shared inversion) */
 int b200_g1_normalize(const b200_g1_xyzz* points, size_t n, b200_g1_jac* out);
 
