@@ -32,6 +32,37 @@ __global__ void k_dbg_digits(const Fr* s, int c, int W, int32_t* out, size_t n) 
     uint32_t carry = 0;
     for (int w = 0; w < W; ++w) out[i * W + w] = msm_next_digit(v.l, c, &carry);
 }
+// ---- throughput microbenchmarks (register-resident loops; results written so nothing is optimised away) ---------
+// variant 0: one dependent chain of Fq mulmods (PTX path); 1: two independent chains; 2: portable C++ mul;
+// 3: chain of XYZZ mixed additions against a register-resident affine point; 4: Fq add/sub chain
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_bench_mul(Fq* out, int iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    Fq x = fp_one<FqTag>(), y = fp_one<FqTag>();
+    x.l[0] ^= t; y.l[1] ^= (t * 2654435761u);
+    if (VARIANT == 0) {
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) x = x * y;
+    } else if (VARIANT == 1) {
+        Fq z = y + y;
+#pragma unroll 1
+        for (int i = 0; i < iters; i += 2) { x = x * y; z = z * y; }
+        x = x + z;
+    } else if (VARIANT == 2) {
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) { Fq r; fp_mul_portable<FqTag>(r.l, x.l, y.l); x = r; }
+    } else if (VARIANT == 3) {
+        G1Affine g; g.x = x; g.y = y;
+        G1Xyzz acc = g1_dbl_affine(g);
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) { acc = g1_add_mixed(acc, g); g.x.l[0] += 1; }
+        x = acc.x + acc.y + acc.zz + acc.zzz;
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) { x = x + y; y = y - x; }
+    }
+    fp_store(out + t, x);
+}
 }  // namespace b200
 using namespace b200;
 
@@ -68,6 +99,26 @@ int b200_debug_digits(const b200_fr* s, size_t n, int c, int32_t* out /* n * cei
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaMemcpy(out, dout, 4 * n * W, cudaMemcpyDeviceToHost));
     cudaFree(ds); cudaFree(dout);
+    return 0;
+}
+// returns elapsed ms for `iters` operations per thread on blocks x threads threads
+int b200_debug_bench(int variant, int iters, int blocks, int threads, float* ms) {
+    Fq* d; B200_CUDA(cudaMalloc(&d, sizeof(Fq) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        switch (variant) {
+            case 0: k_bench_mul<0><<<blocks, threads>>>(d, iters); break;
+            case 1: k_bench_mul<1><<<blocks, threads>>>(d, iters); break;
+            case 2: k_bench_mul<2><<<blocks, threads>>>(d, iters); break;
+            case 3: k_bench_mul<3><<<blocks, threads>>>(d, iters); break;
+            default: k_bench_mul<4><<<blocks, threads>>>(d, iters); break;
+        }
+        cudaEventRecord(e1);
+        B200_CUDA(cudaEventSynchronize(e1));
+    }
+    B200_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }
 // host-only: the same recoding routine compiled for the CPU (lets the not-gpu tests check it without a device)

@@ -286,3 +286,15 @@ def test_error_behaviour():
     out = np.zeros(12, np.uint64)
     assert L.b200_msm(C.c_uint64(987654), nat.ptr(a), C.c_size_t(2), nat.ptr(out)) == -1
     assert b"unknown bases handle" in L.b200_last_error()
+
+
+def test_cpp_host_mirror():
+    """include/ezkl_b200_halo2.hpp (C++ mirror of EvaluationDomain / ParamsKZG) against the reference's SRS fixture."""
+    import os
+    import subprocess
+    exe = os.path.join(H.ROOT, "tests", "cpp", "test_mirror")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(H.ROOT, "include"), "-o", exe, os.path.join(H.ROOT, "tests", "cpp", "test_mirror.cpp"),
+                               "-L" + os.path.join(H.ROOT, "ezkl_b200"), "-lezkl_b200", "-Wl,-rpath," + os.path.join(H.ROOT, "ezkl_b200")])
+    r = subprocess.run([exe, os.path.join(H.GOLDEN, "kzg_k6.srs")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
