@@ -12,6 +12,7 @@
 // the store.  Coset pre-scaling (zeta^(i mod 3)), zero padding and the 1/N (and zeta^-(i mod 3)) post-scaling of the
 // extended-domain transforms are fused into the first load / last store.  Algorithmic HBM traffic: 64 B per element per
 // transform; this schedule moves 64 B per element per PASS (2 passes up to 2^20, 3 above).
+#include <cstdlib>
 #include "ntt.cuh"
 
 namespace b200 {
@@ -162,10 +163,12 @@ static int launch_pass(PassArgs& a, uint64_t lines, int batch, cudaStream_t st) 
     uint32_t log_g = 2;
     while (log_g > 0 && ((1u << log_g) > a.inner_cnt || (lines >> log_g) * (uint64_t)batch < 296)) --log_g;
     while (log_g > 0 && (((size_t)1 << (a.logm + log_g)) + ((size_t)1 << a.logm) / 2) * 32 > 200 * 1024) --log_g;
+    if (const char* e = getenv("B200_NTT_LOGG")) { uint32_t v = (uint32_t)atoi(e); while (v > 0 && (1u << v) > a.inner_cnt) --v; log_g = v; }
     a.log_g = log_g;
     const size_t smem = (((size_t)1 << (a.logm + log_g)) + (((size_t)1 << a.logm) >> 1)) * 32;
     const uint32_t nbf = (1u << (a.logm + log_g)) >> 1;
     uint32_t threads = nbf < 32 ? 32 : (nbf > 1024 ? 1024 : nbf);
+    if (const char* e = getenv("B200_NTT_THREADS")) { uint32_t v = (uint32_t)atoi(e); if (v >= 32 && v <= 1024 && v < threads) threads = v; }
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

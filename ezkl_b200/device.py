@@ -17,7 +17,10 @@ from . import fields as F
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream as a cudaStream_t.  The legacy default stream has handle 0, which the C ABI reads as "use the
+    library's own stream"; pass CUDA's explicit cudaStreamLegacy handle (0x1) instead so ordering and event timing hold."""
+    h = torch.cuda.current_stream().cuda_stream
+    return C.c_void_p(h if h else 1)
 
 
 def _chk(t: torch.Tensor, last: int):
