@@ -12,6 +12,7 @@
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "poly.cuh"
+#include "quotient.cuh"
 
 namespace b200 {
 
@@ -37,6 +38,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     MsmWorkspace msm_ws;
     PolyWorkspace poly_ws;
+    QuotientWorkspace quot_ws;
     DevBuf stage_a, stage_b, stage_c, small;
     bool ok = false;
 };
@@ -507,6 +509,44 @@ int b200_kate_division(const b200_fr* a, size_t n, const b200_fr* b, b200_fr* q)
     B200_CUDA(cudaMemcpyAsync(c->stage_a.p, a, sizeof(Fr) * n, cudaMemcpyHostToDevice, c->stream));
     if (int rc = b200_kate_division_dev(c->stage_a.p, n, b, c->stage_b.p, nullptr)) return rc;
     B200_CUDA(cudaMemcpyAsync(q, c->stage_b.p, sizeof(Fr) * (n - 1), cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- quotient numerator (evaluate_h) ------------------------------------------------------------------------------
+static_assert(sizeof(b200_instr) == sizeof(QInstr) && sizeof(b200_col_ref) == sizeof(QLoad), "ABI structs must match the kernel's");
+int b200_quotient_eval_dev(const void* const* d_columns, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_col_ref* loads, size_t n_loads,
+                           const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr, void* d_out, void* stream) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(d_out && (n_columns == 0 || d_columns) && (n_loads == 0 || loads) && (n_constants == 0 || constants) && (n_instr == 0 || program), -1, "quotient_eval: null pointer");
+    B200_CHECK(ext_k >= k && ext_k <= 28, -1, "quotient_eval: need k <= ext_k <= 28");
+    const uint64_t N = 1ull << ext_k, scale = 1ull << (ext_k - k);
+    std::vector<QLoad> ql(n_loads);
+    for (size_t i = 0; i < n_loads; ++i) {
+        ql[i].column = loads[i].column;
+        const int64_t off = (int64_t)loads[i].rotation * (int64_t)scale;           // Rotation(r) on the extended domain = r * 2^(ext_k - k)
+        ql[i].offset = (uint32_t)(((off % (int64_t)N) + (int64_t)N) % (int64_t)N);
+    }
+    int rc = quotient_eval_run(reinterpret_cast<const Fr* const*>(d_columns), n_columns, ext_k, ql.data(), n_loads, reinterpret_cast<const Fr*>(constants), n_constants,
+                               reinterpret_cast<const QInstr*>(program), n_instr, reinterpret_cast<Fr*>(d_out), c->quot_ws, pick_stream(c, stream));
+    if (!rc) g_launches += 1;
+    return rc;
+}
+int b200_quotient_eval(const b200_fr* const* columns, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_col_ref* loads, size_t n_loads,
+                       const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr, b200_fr* out) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(out && (n_columns == 0 || columns), -1, "quotient_eval: null pointer");
+    B200_CHECK(ext_k >= 1 && ext_k <= 28, -1, "quotient_eval: ext_k out of range");
+    const size_t N = (size_t)1 << ext_k;
+    if (c->stage_a.ensure(sizeof(Fr) * N * (n_columns ? n_columns : 1)) || c->stage_b.ensure(sizeof(Fr) * N)) return -2;
+    std::vector<const void*> ptrs(n_columns);
+    for (size_t i = 0; i < n_columns; ++i) {
+        B200_CHECK(columns[i], -1, "quotient_eval: column %zu is null", i);
+        ptrs[i] = c->stage_a.as<Fr>() + i * N;
+        B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + i * N, columns[i], sizeof(Fr) * N, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (int rc = b200_quotient_eval_dev(ptrs.data(), n_columns, k, ext_k, loads, n_loads, constants, n_constants, program, n_instr, c->stage_b.p, nullptr)) return rc;
+    B200_CUDA(cudaMemcpyAsync(out, c->stage_b.p, sizeof(Fr) * N, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }

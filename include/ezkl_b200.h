@@ -111,6 +111,21 @@ int b200_prefix_scan_dev(int product, const void* d_a, size_t n, const b200_fr* 
 int b200_kate_division(const b200_fr* a, size_t n, const b200_fr* b, b200_fr* q);
 int b200_kate_division_dev(const void* d_a, size_t n, const b200_fr* b, void* d_q, void* stream);
 
+/* ---- quotient numerator: halo2 plonk/evaluation.rs Evaluator::evaluate_h (GraphEvaluator) -------------------------
+ * A straight-line program of field operations evaluated once per row of the extended domain:
+ *   out[idx] = program(columns[c][(idx + rotation * 2^(ext_k - k)) mod 2^ext_k], constants).
+ * Operand encoding (b200_instr.a / .b): bits 31..30 kind — 0 slot (result register, < 32), 1 constants[index],
+ * 2 loads[index] — bits 29..0 index.  op_dst = op | (dst_slot << 8); op: 0 add, 1 sub, 2 mul, 3 neg(a), 4 double(a),
+ * 5 square(a), 6 mov(a).  The row's result is the destination of the last instruction.  Gates, permutation and lookup terms,
+ * l0 / l_last / l_active_row, the identity coset and earlier partial sums are all just columns; y, beta, gamma, theta are
+ * constants.  Columns are 2^ext_k elements each. */
+typedef struct { uint32_t op_dst; uint32_t a, b; } b200_instr;
+typedef struct { uint32_t column; int32_t rotation; } b200_col_ref;
+int b200_quotient_eval(const b200_fr* const* columns, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_col_ref* loads, size_t n_loads,
+                       const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr, b200_fr* out);
+int b200_quotient_eval_dev(const void* const* d_columns, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_col_ref* loads, size_t n_loads,
+                           const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr, void* d_out, void* stream);
+
 /* ---- device / pinned memory helpers for callers without their own CUDA runtime ---------------------------------- */
 int b200_dev_alloc(void** d_ptr, size_t bytes);
 int b200_dev_free(void* d_ptr);

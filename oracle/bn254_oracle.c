@@ -491,3 +491,44 @@ API void orc_prefix_scan(int is_product, const fe *a, size_t n, const fe *init, 
     fe acc = *init;
     for (size_t i = 0; i < n; ++i) { out[i] = acc; if (is_product) R_MUL(&acc, &acc, &a[i]); else R_ADD(&acc, &acc, &a[i]); }
 }
+
+/* ---- evaluate_h: the quotient-numerator interpreter (UPSTREAM plonk/evaluation.rs GraphEvaluator::evaluate, restated for the
+ * instruction format of include/ezkl_b200.h: b200_instr / b200_col_ref).  Row-parallel over threads like halo2's parallelize. */
+typedef struct { const fe *const *cols; uint32_t k, ext_k; const uint32_t *loads; const fe *consts; const uint32_t *prog; size_t n_instr; fe *out; } qe_job;
+static inline const fe *qe_src(const qe_job *j, uint32_t s, const fe *slots, size_t idx, fe *tmp) {
+    uint32_t kind = s >> 30, i = s & 0x3fffffffu;
+    if (kind == 0) return &slots[i];
+    if (kind == 1) return &j->consts[i];
+    uint64_t N = (uint64_t)1 << j->ext_k; int64_t scale = (int64_t)1 << (j->ext_k - j->k);
+    int64_t rot = (int32_t)j->loads[2 * i + 1];
+    int64_t off = ((rot * scale) % (int64_t)N + (int64_t)N) % (int64_t)N;
+    *tmp = j->cols[j->loads[2 * i]][(idx + (uint64_t)off) & (N - 1)];
+    return tmp;
+}
+static void qe_worker(void *arg, int tid, int nt) {
+    qe_job *j = (qe_job *)arg;
+    size_t N = (size_t)1 << j->ext_k, chunk = (N + nt - 1) / nt, lo = chunk * tid, hi = lo + chunk; if (hi > N) hi = N;
+    fe slots[32], ta, tb;
+    for (size_t idx = lo; idx < hi; ++idx) {
+        uint32_t last = 0;
+        for (size_t pc = 0; pc < j->n_instr; ++pc) {
+            uint32_t op = j->prog[3 * pc] & 0xff, dst = (j->prog[3 * pc] >> 8) & 31;
+            const fe *x = qe_src(j, j->prog[3 * pc + 1], slots, idx, &ta);
+            fe r;
+            if (op <= 2) {
+                const fe *y = qe_src(j, j->prog[3 * pc + 2], slots, idx, &tb);
+                if (op == 0) R_ADD(&r, x, y); else if (op == 1) R_SUB(&r, x, y); else R_MUL(&r, x, y);
+            } else if (op == 3) f_neg(&r, x, FR_M);
+            else if (op == 4) R_ADD(&r, x, x);
+            else if (op == 5) R_MUL(&r, x, x);
+            else r = *x;
+            slots[dst] = r; last = dst;
+        }
+        if (j->n_instr) j->out[idx] = slots[last]; else memset(&j->out[idx], 0, sizeof(fe));
+    }
+}
+API void orc_quotient_eval(const fe *const *cols, uint32_t k, uint32_t ext_k, const uint32_t *loads, const fe *consts, const uint32_t *prog, size_t n_instr,
+                           fe *out, int threads) {
+    qe_job j = {cols, k, ext_k, loads, consts, prog, n_instr, out};
+    run_threads(qe_worker, &j, threads < 1 ? 1 : threads);
+}

@@ -1,0 +1,120 @@
+"""evaluate_h: the expression compiler (host logic, CPU) and the device interpreter against the oracle's interpreter (GPU)."""
+import random
+
+import numpy as np
+import pytest
+
+from ezkl_b200 import evaluation as ev
+from ezkl_b200 import fields as F
+from oracle import oracle as orc
+from oracle import pyref
+from tests import helpers as H
+
+R = pyref.R
+
+
+def random_expr(rng, ncols, depth):
+    if depth == 0 or rng.random() < 0.15:
+        if rng.random() < 0.3:
+            return ev.Constant(rng.randrange(R))
+        return ev.Query(rng.randrange(ncols), rng.choice([0, 0, 1, -1, 2, -3]))
+    c = rng.random()
+    a = random_expr(rng, ncols, depth - 1)
+    if c < 0.15:
+        return -a
+    if c < 0.25:
+        return a * a
+    b = random_expr(rng, ncols, depth - 1)
+    return a + b if c < 0.5 else (a - b if c < 0.65 else a * b)
+
+
+def eval_tree(e, cols, idx, n, scale):
+    if e.kind == "constant":
+        return e.args[0]
+    if e.kind == "query":
+        return cols[e.args[0]][(idx + e.args[1] * scale) % n]
+    v = [eval_tree(a, cols, idx, n, scale) for a in e.args]
+    return {"sum": lambda: v[0] + v[1], "sub": lambda: v[0] - v[1], "product": lambda: v[0] * v[1], "negated": lambda: -v[0]}[e.kind]() % R
+
+
+def test_compiler_matches_tree_semantics_and_oracle():
+    rng = random.Random(2)
+    k, ext_k, ncols = 3, 5, 4
+    N, scale = 1 << ext_k, 1 << (ext_k - k)
+    cols_int = [[rng.randrange(R) for _ in range(N)] for _ in range(ncols)]
+    cols = [H.fr_array(c) for c in cols_int]
+    for trial in range(25):
+        e = random_expr(rng, ncols, 5)
+        prog = ev.QuotientProgram(e)
+        assert all(dst < ev.MAX_SLOTS for _, dst, _, _ in prog.instrs)
+        loads, consts, instrs = prog.arrays()
+        got = H.fr_list(orc.quotient_eval(cols, k, ext_k, loads, consts, instrs, threads=2))
+        for idx in (0, 1, N - 1, rng.randrange(N)):
+            exp = eval_tree(e, cols_int, idx, N, scale)
+            assert prog.evaluate_ints(cols_int, idx, N, scale) == exp
+            assert got[idx] == exp
+    # bare leaves and shared sub-expressions
+    q = ev.Query(1, 1)
+    for e in (q, ev.Constant(5), (q + 1) * (q + 1) - (q + 1)):
+        prog = ev.QuotientProgram(e)
+        loads, consts, instrs = prog.arrays()
+        got = H.fr_list(orc.quotient_eval(cols, k, ext_k, loads, consts, instrs))
+        assert got[3] == eval_tree(e, cols_int, 3, N, scale)
+    assert len(ev.QuotientProgram((q + 1) * (q + 1) - (q + 1)).instrs) == 3      # (q+1) computed once, squared, subtracted
+
+
+@pytest.mark.gpu
+def test_device_interpreter_vs_oracle():
+    from ezkl_b200 import _native as nat
+    nat.init(-1)
+    rng = random.Random(4)
+    for k, ext_k, ncols in ((4, 6, 3), (10, 13, 8), (13, 15, 12)):
+        N = 1 << ext_k
+        cols = [orc.gen_scalars(N, seed=100 * k + i) for i in range(ncols)]
+        for trial in range(4):
+            prog = ev.QuotientProgram(random_expr(rng, ncols, 6 + trial))
+            loads, consts, instrs = prog.arrays()
+            got = ev.evaluate_h(prog, cols, k, ext_k)
+            assert np.array_equal(got, orc.quotient_eval(cols, k, ext_k, loads, consts, instrs, threads=orc.host_threads())), (k, trial)
+
+
+@pytest.mark.gpu
+def test_quotient_pipeline_on_a_satisfied_gate():
+    """End-to-end property on a tiny PLONK-style circuit (q_m*a*b + q_c - c = 0 on every row, plus a rotation term
+    a(wX) - d = 0): the GPU pipeline iNTT -> coset NTT -> evaluate_h -> divide_by_vanishing -> extended_to_coeff must give
+    h with  numerator(x) == h(x) * (x^n - 1)  at a random point, and h of degree < n*(deg-1)."""
+    from ezkl_b200 import _native as nat
+    from ezkl_b200 import halo2 as h2
+    nat.init(-1)
+    rng = random.Random(9)
+    k = 8
+    n = 1 << k
+    dom = h2.EvaluationDomain(4, k)          # degree-3 gate -> quotient_poly_degree 3 -> extended_k = k + 2
+    ext_k = dom.extended_k
+    a = [rng.randrange(R) for _ in range(n)]
+    b = [rng.randrange(R) for _ in range(n)]
+    qm = [rng.randrange(R) for _ in range(n)]
+    qc = [rng.randrange(R) for _ in range(n)]
+    c = [(qm[i] * a[i] * b[i] + qc[i]) % R for i in range(n)]
+    d = [a[(i + 1) % n] for i in range(n)]
+    y = rng.randrange(R)
+    lag = [H.fr_array(v) for v in (a, b, c, d, qm, qc)]
+    coeffs = dom.lagrange_to_coeff_batch(lag)
+    cosets = dom.coeff_to_extended_batch(coeffs)
+    A, B, Cc, D, QM, QC = (ev.Query(i) for i in range(6))
+    gate1 = QM * A * B + QC - Cc
+    gate2 = ev.Query(0, 1) - D
+    expr = gate1 * ev.Constant(y) + gate2               # fold with y like evaluate_h does
+    prog = ev.QuotientProgram(expr)
+    num_ext = ev.evaluate_h(prog, cosets, k, ext_k)
+    h_ext = dom.divide_by_vanishing_poly(num_ext)
+    h = dom.extended_to_coeff(h_ext)
+    assert h.shape[0] == n * 3
+    assert not h[2 * n:].any()                          # deg(numerator) <= 3(n-1)  =>  deg(h) < 2n
+    x = rng.randrange(R)
+    xv = H.fr_wire(x)
+    ev_at = [H.fr_unwire(h2.eval_polynomial(p, xv)) for p in coeffs]
+    a_rot = H.fr_unwire(h2.eval_polynomial(coeffs[0], H.fr_wire(x * pyref.omega_for(k) % R)))
+    numerator = ((ev_at[4] * ev_at[0] * ev_at[1] + ev_at[5] - ev_at[2]) * y + (a_rot - ev_at[3])) % R
+    hx = H.fr_unwire(h2.eval_polynomial(h, xv))
+    assert numerator == hx * (pow(x, n, R) - 1) % R
