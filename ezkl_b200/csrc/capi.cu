@@ -56,7 +56,8 @@ static int get_ctx(Ctx** out) {
     return 0;
 }
 static inline cudaStream_t pick_stream(Ctx* c, void* user) { return user ? (cudaStream_t)user : c->stream; }
-static inline const Fr& as_fr(const b200_fr* p) { return *reinterpret_cast<const Fr*>(p); }
+// host Fr values arrive with 8-byte alignment (Rust / C callers); Fr is alignas(16), so always copy bytewise
+static inline Fr as_fr(const b200_fr* p) { Fr r; memcpy(&r, p, sizeof r); return r; }
 
 // XYZZ (host) -> normalised Jacobian, one shared inversion (Montgomery's trick over zz*zzz)
 static void normalize_host(const G1Xyzz* pts, size_t n, b200_g1_jac* out) {
@@ -394,7 +395,9 @@ int b200_poly_op_dev(int op, const void* d_a, const void* d_b, const b200_fr* s,
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(op >= 0 && op <= 4, -1, "poly_op: unknown op %d", op);
     B200_CHECK(d_a && d_out && (op == POLY_SCALE || d_b) && (op < POLY_SCALE || s), -1, "poly_op: missing operand for op %d", op);
-    int rc = poly_binary(op, reinterpret_cast<const Fr*>(d_a), reinterpret_cast<const Fr*>(d_b), reinterpret_cast<const Fr*>(s), reinterpret_cast<Fr*>(d_out), n, pick_stream(c, stream));
+    Fr sv = fp_zero<FrTag>();
+    if (s) sv = as_fr(s);
+    int rc = poly_binary(op, reinterpret_cast<const Fr*>(d_a), reinterpret_cast<const Fr*>(d_b), s ? &sv : nullptr, reinterpret_cast<Fr*>(d_out), n, pick_stream(c, stream));
     if (!rc && n) g_launches += 1;
     return rc;
 }
@@ -437,7 +440,9 @@ int b200_poly_eval_batch_dev(const void* d_polys, size_t stride, size_t n, const
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(d_polys && x && d_out, -1, "poly_eval: null pointer");
     if (batch == 0) return 0;
-    int rc = poly_eval(reinterpret_cast<const Fr*>(d_polys), stride, n, reinterpret_cast<const Fr*>(x), reinterpret_cast<Fr*>(d_out), (int)batch, c->poly_ws, pick_stream(c, stream));
+    std::vector<Fr> xv(batch);
+    memcpy(xv.data(), x, sizeof(Fr) * batch);
+    int rc = poly_eval(reinterpret_cast<const Fr*>(d_polys), stride, n, xv.data(), reinterpret_cast<Fr*>(d_out), (int)batch, c->poly_ws, pick_stream(c, stream));
     if (!rc && n) g_launches += 2;
     return rc;
 }
@@ -478,7 +483,8 @@ int b200_batch_invert(b200_fr* a, size_t n) {
 int b200_prefix_scan_dev(int product, const void* d_a, size_t n, const b200_fr* init, void* d_out, void* stream) {
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(d_a && init && d_out, -1, "prefix_scan: null pointer");
-    int rc = poly_prefix_scan(product != 0, reinterpret_cast<const Fr*>(d_a), n, reinterpret_cast<const Fr*>(init), reinterpret_cast<Fr*>(d_out), c->poly_ws, pick_stream(c, stream));
+    const Fr iv = as_fr(init);
+    int rc = poly_prefix_scan(product != 0, reinterpret_cast<const Fr*>(d_a), n, &iv, reinterpret_cast<Fr*>(d_out), c->poly_ws, pick_stream(c, stream));
     if (!rc && n) g_launches += 3;
     return rc;
 }
@@ -496,7 +502,8 @@ int b200_prefix_scan(int product, const b200_fr* a, size_t n, const b200_fr* ini
 int b200_kate_division_dev(const void* d_a, size_t n, const b200_fr* b, void* d_q, void* stream) {
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(d_a && b && d_q, -1, "kate_division: null pointer");
-    int rc = poly_kate_division(reinterpret_cast<const Fr*>(d_a), n, reinterpret_cast<const Fr*>(b), reinterpret_cast<Fr*>(d_q), c->poly_ws, pick_stream(c, stream));
+    const Fr bv = as_fr(b);
+    int rc = poly_kate_division(reinterpret_cast<const Fr*>(d_a), n, &bv, reinterpret_cast<Fr*>(d_q), c->poly_ws, pick_stream(c, stream));
     if (!rc && n > 1) g_launches += 3;
     return rc;
 }
