@@ -2,12 +2,15 @@
 """bench.py — prove-trace replay of the Halo2/KZG prover hot path on B200 (BASELINE.json metric: prove time (s) at k;
 MSM G1 pairs/s and NTT Fr elts/s vs the HBM roofline).
 
-A "step" is ONE proof's worth of hot-path work (SURVEY.md §3.1 stages 1-9 minus synthesize / transcript / evaluate_h,
-which are outside this round's kernels — see DESIGN.md): the MSMs, (i)NTTs, coset NTTs and column-polynomial passes one
-`create_proof` issues for a circuit of the shape named in `config.workload`, on synthetic seeded columns.
+A "step" is ONE proof's worth of hot-path work (SURVEY.md §3.1 stages 1-9 minus synthesize / transcript, which stay on the
+CPU in Rust — see DESIGN.md): the MSMs, (i)NTTs, coset NTTs, the quotient-numerator evaluation (evaluate_h, a synthetic
+gate program touching every coset column at three rotations) and the column-polynomial passes one `create_proof` issues
+for a circuit of the shape named in `config.workload`, on synthetic seeded columns.
   * `value`   : seconds per proof with all columns resident in HBM (device entry points), CUDA-event timed.
-  * `e2e`     : the same trace through the host-buffer C ABI (what the halo2 shim calls): pinned host columns in, results
-                back in host memory, H2D/D2H inside the timed region.
+  * `e2e`     : the same trace through the C ABI starting from HOST buffers: each witness-derived column is uploaded once from
+                pinned host memory (b200_dev_upload), later stages use the device-pointer entry points (the resident-column
+                shim of INTEGRATION.md §2b), commitments are normalised on the host and evaluations read back; H2D/D2H and
+                the host tail are inside the timed region.
   * `roofline`: the dominant kernel (MSM bucket accumulation) against the measured HBM peak, timed with CUDA events
                 inside the library on the launching stream.
   * `cpu_baseline` / `--impl reference`: the CPU restatement of halo2's Rayon algorithms (oracle/, "port") on the box's
@@ -54,9 +57,7 @@ def trace_ops(tr):
         ("msm_lagrange", Z + L),                    #          commitments to z's and phi's
         ("msm_coeff", 1),                           # stage 4: vanishing random polynomial
         ("intt", ncoset),                           # stage 5: Lagrange -> coefficients
-        ("coset_ntt", ncoset),                      # stage 6: coefficients -> extended coset (evaluate_h itself: not replayed)
-        ("divide_vanishing", 1),                    # stage 7
-        ("ext_intt", 1),
+        ("quotient", 1),                            # stages 6-7: ncoset coset NTTs -> evaluate_h -> divide by vanishing -> extended iNTT
         ("msm_coeff", Q),
         ("eval", tr["evals"]),                      # stage 8
         ("axpy", npolys),                           # stage 9: SHPLONK linear combinations
@@ -65,10 +66,30 @@ def trace_ops(tr):
     ]
 
 
-def count_units(ops, n, ext_bits):
+def n_coset_columns(tr):
+    return tr["advice"] + tr["instance"] + tr["perm_z"] + 2 * tr["lookups"]
+
+
+def count_units(ops, n, tr):
     pairs = sum(c for k, c in ops if k.startswith("msm")) * n
-    ntt_elts = sum(c * (n if k == "intt" else (n << ext_bits)) for k, c in ops if k in ("intt", "coset_ntt", "ext_intt"))
+    ntt_elts = sum(c * n for k, c in ops if k == "intt") + (n_coset_columns(tr) + 1) * (n << tr["ext_bits"])
     return pairs, ntt_elts
+
+
+QUOTIENT_GROUP = 32          # coset columns evaluated per evaluate_h call (partial sums carried in h)
+GATE_Y = 0x1234567890ABCDEF1234567890ABCDEF
+
+
+def gate_program(m):
+    """Synthetic gate set over m coset columns + the running sum h (column m): for every column t one degree-2 term reading
+    three columns at rotations 0 / +1 / -1, folded with y exactly like evaluate_h folds gates:  h <- h*y + (a*b + c*a - b)."""
+    from ezkl_b200 import evaluation as ev
+    value = ev.Query(m)
+    y = ev.Constant(GATE_Y)
+    for t in range(m):
+        a, b, c = ev.Query(t), ev.Query((t + 1) % m, 1), ev.Query((t + 2) % m, -1)
+        value = value * y + (a * b + c * a - b)
+    return ev.QuotientProgram(value)
 
 
 class ClockSampler(threading.Thread):
@@ -134,9 +155,6 @@ def run_b200(args):
     ncols = max(c for _, c in ops if True)
     ncols = min(ncols, 64)                                      # column pool; ops cycle through it
     cols = dev.random_scalars(n, batch=ncols, seed=1234 + rank)
-    ext_chunk = max(1, min(16, (4 << 30) // (32 << ext_k)))     # extended columns processed per call
-    ext_buf = torch.empty((ext_chunk, 1 << ext_k, 4), dtype=torch.int64, device="cuda")
-    ext_tmp = torch.empty_like(ext_buf)
     tmp_n = torch.empty((ncols, n, 4), dtype=torch.int64, device="cuda")
     out_n = torch.empty((ncols, n, 4), dtype=torch.int64, device="cuda")
     xs = dev.to_host(dev.random_scalars(ncols, seed=99))
@@ -146,26 +164,83 @@ def run_b200(args):
     post_ext = [F.fr_to_limbs(d), F.fr_to_limbs(d * F.FR_ZETA * F.FR_ZETA % F.FR_MODULUS), F.fr_to_limbs(d * F.FR_ZETA % F.FR_MODULUS)]
     host_cols = torch.empty((ncols, n, 4), dtype=torch.int64).pin_memory()
     host_cols.copy_(cols.cpu())
-    host_ext = torch.empty((1 << ext_k, 4), dtype=torch.int64).pin_memory()
-    host_out = torch.empty((ncols, n, 4), dtype=torch.int64).pin_memory()
+    host_evals = torch.empty((max(ncols, 256), 4), dtype=torch.int64).pin_memory()
 
     def mine(count, base):
         """op instances of one group owned by this rank (round-robin over a running global index)."""
         return [i for i in range(count) if par.column_owner(base + i, world) == rank]
 
+    from ezkl_b200 import evaluation as ev
+    ncoset = n_coset_columns(tr)
+    log_g = world.bit_length() - 1
+    assert world == 1 << log_g and world <= (1 << tr["ext_bits"]), "quotient stage: world must be a power of two <= 2^ext_bits"
+    N_ext = 1 << ext_k
+    slab = N_ext // world
+    group = QUOTIENT_GROUP if ext_k <= 23 else 16
+    programs = {}
+    d_ext = 1 << tr["ext_bits"]
+    tinv_local = np.ascontiguousarray(np.stack([dom.t_evaluations[(rank + world * t) % d_ext] for t in range(max(1, d_ext // world))]))
+    host_h = torch.empty((tr["quotient_pieces"] * n, 4), dtype=torch.int64).pin_memory()
+
+    def quotient_stage(get_col, put_h):
+        """Stages 6-7.  Coset NTTs are dealt by column; evaluate_h runs row-cyclic (row idx on rank idx mod world): since
+        world divides 2^ext_bits every Rotation(r) = r * 2^ext_bits rows stays on its rank, so the only exchange is one
+        all-to-all per column group; h slabs are all-gathered once for the single extended iNTT on rank 0."""
+        h = torch.zeros((slab, 4), dtype=torch.int64, device="cuda")
+        for g0 in range(0, ncoset, group):
+            gcols = list(range(g0, min(ncoset, g0 + group)))
+            my = [j for j in gcols if par.column_owner(j, world) == rank]
+            if my:
+                src = torch.stack([get_col(j) for j in my])
+                ext_my = dev.ntt(src, ext_k, dom.extended_omega, n_in=n, pre=[one, zeta, zeta2])
+            else:
+                ext_my = torch.empty((0, N_ext, 4), dtype=torch.int64, device="cuda")
+            if world > 1:
+                view = ext_my.view(len(my), slab, world, 4)
+                send = [view[:, :, s_].contiguous() for s_ in range(world)]
+                counts = [len([j for j in gcols if par.column_owner(j, world) == q]) for q in range(world)]
+                recv = [torch.empty((counts[q], slab, 4), dtype=torch.int64, device="cuda") for q in range(world)]
+                dist.all_to_all(recv, send)
+                by_col = {}
+                for q in range(world):
+                    for i_, j in enumerate([j for j in gcols if par.column_owner(j, world) == q]):
+                        by_col[j] = recv[q][i_]
+                slabs = [by_col[j] for j in gcols]
+            else:
+                slabs = [ext_my[i_] for i_ in range(len(my))]
+            m = len(gcols)
+            if m not in programs:
+                programs[m] = gate_program(m)
+            h = ev.evaluate_h_device(programs[m], slabs + [h], k, ext_k - log_g)
+        dev.scale_cycle(h, tinv_local)
+        if world > 1:
+            parts = [torch.empty_like(h) for _ in range(world)]
+            dist.all_gather(parts, h)
+            full = torch.stack(parts, dim=1).reshape(1, N_ext, 4).contiguous()      # idx = t*world + rank
+        else:
+            full = h.view(1, N_ext, 4)
+        if rank == 0:
+            coeff = dev.ntt(full, ext_k, dom.extended_omega_inv, post=post_ext)
+            if put_h is not None:
+                put_h(coeff[0, : tr["quotient_pieces"] * n])
+
     commits = []
 
-    def step_device():
-        """One proof's trace with device-resident columns."""
+    evals = []
+
+    def step_device(pool=None):
+        """One proof's trace with device-resident columns (pool defaults to the resident synthetic columns)."""
+        cols_ = cols if pool is None else pool
         commits.clear()
+        evals.clear()
         gidx = 0
         for kind, count in ops:
-            m = len(mine(count, gidx))
+            m = len(mine(count, gidx)) if kind != "quotient" else 1     # the quotient stage is cooperative: every rank takes part
             gidx += count
             done = 0
             while done < m:
                 b = min(m - done, ncols)
-                v = cols[:b]
+                v = cols_[:b]
                 if kind == "msm_lagrange":
                     commits.append(dev.msm_batch(g_lag, v))
                 elif kind == "msm_coeff":
@@ -181,18 +256,10 @@ def run_b200(args):
                         dev.prefix_scan(v[i], one, False, out=out_n[i])
                 elif kind == "intt":
                     dev.ntt(v, k, dom.omega_inv, post=[dom.ifft_divisor], out=out_n[:b], tmp=tmp_n[:b])
-                elif kind == "coset_ntt":
-                    for c0 in range(0, b, ext_chunk):
-                        cb = min(ext_chunk, b - c0)
-                        dev.ntt(v[c0:c0 + cb], ext_k, dom.extended_omega, n_in=n, pre=[one, zeta, zeta2], out=ext_buf[:cb], tmp=ext_tmp[:cb])
-                elif kind == "divide_vanishing":
-                    for _ in range(b):
-                        dev.scale_cycle(ext_buf[0], dom.t_evaluations)
-                elif kind == "ext_intt":
-                    for _ in range(b):
-                        dev.ntt(ext_buf[:1], ext_k, dom.extended_omega_inv, post=post_ext, out=ext_buf[:1], tmp=ext_tmp[:1])
+                elif kind == "quotient":
+                    quotient_stage(lambda j: cols_[j % ncols], None)
                 elif kind == "eval":
-                    dev.eval_batch(v, xs[:b])
+                    evals.append(dev.eval_batch(v, xs[:b]))
                 elif kind == "axpy":
                     for i in range(b):
                         dev.poly_op("axpy", out_n[0], v[i], s=xs[i], out=out_n[0])
@@ -210,65 +277,26 @@ def run_b200(args):
 
     L = nat.lib()
     import ctypes as C
+    e2e_pool = torch.empty_like(cols)
+    n_inputs = tr["advice"] + tr["instance"] + tr["lookups"] + 1      # witness-derived columns that exist only on the host before a proof
 
     def step_host():
-        """The same trace through the host-buffer C ABI (pinned host memory in and out)."""
-        hc = host_cols.numpy().view(np.uint64)
-        ho = host_out.numpy().view(np.uint64)
-        he = host_ext.numpy().view(np.uint64)
+        """End to end through the C ABI from HOST buffers: every witness-derived column crosses PCIe once (b200_dev_upload from
+        pinned memory into a device-resident column), all later stages use the device-pointer entry points, and the step's
+        results come back to the host: commitments (XYZZ -> b200_g1_normalize on the host) and the evaluations."""
+        my_inputs = [i for i in range(n_inputs) if par.column_owner(i, world) == rank] if world > 1 else list(range(n_inputs))
         h2d = d2h = 0
-        gidx = 0
-        res = []
-        for kind, count in ops:
-            m = len(mine(count, gidx))
-            gidx += count
-            done = 0
-            while done < m:
-                b = min(m - done, ncols)
-                v = [hc[i] for i in range(b)]
-                if kind in ("msm_lagrange", "msm_coeff"):
-                    res.append(h2.best_multiexp_batch(v, _HostBases(g_lag if kind == "msm_lagrange" else g_coef)))
-                    h2d += b * n * 32; d2h += b * 128
-                elif kind == "batch_invert":
-                    for i in range(b):
-                        nat.check(L.b200_batch_invert(nat.ptr(hc[i]), C.c_size_t(n)))
-                    h2d += b * n * 32; d2h += b * n * 32
-                elif kind in ("prefix_product", "prefix_sum"):
-                    for i in range(b):
-                        nat.check(L.b200_prefix_scan(C.c_int(1 if kind == "prefix_product" else 0), nat.ptr(hc[i]), C.c_size_t(n), nat.ptr(one), nat.ptr(ho[i])))
-                    h2d += b * n * 32; d2h += b * n * 32
-                elif kind == "intt":
-                    nat.check(L.b200_ifft_batch(nat.ptr_array(v), C.c_size_t(b), C.c_uint32(k), nat.ptr(dom.omega_inv), nat.ptr(dom.ifft_divisor)))
-                    h2d += b * n * 32; d2h += b * n * 32
-                elif kind == "coset_ntt":
-                    for i in range(b):
-                        nat.check(L.b200_coeff_to_extended(nat.ptr(hc[i]), C.c_size_t(n), C.c_uint32(ext_k), nat.ptr(dom.extended_omega), nat.ptr(dom.g_coset), nat.ptr(he)))
-                    h2d += b * n * 32; d2h += b * (32 << ext_k)
-                elif kind == "divide_vanishing":
-                    for _ in range(b):
-                        nat.check(L.b200_poly_scale_cycle(nat.ptr(he), C.c_size_t(1 << ext_k), nat.ptr(dom.t_evaluations), C.c_uint32(dom.t_evaluations.shape[0])))
-                    h2d += b * (32 << ext_k); d2h += b * (32 << ext_k)
-                elif kind == "ext_intt":
-                    for _ in range(b):
-                        nat.check(L.b200_extended_to_coeff(nat.ptr(he), C.c_uint32(ext_k), nat.ptr(dom.extended_omega_inv), nat.ptr(dom.extended_ifft_divisor), nat.ptr(dom.g_coset)))
-                    h2d += b * (32 << ext_k); d2h += b * (32 << ext_k)
-                elif kind == "eval":
-                    res.append(h2.eval_polynomial_batch(v, xs[:b]))
-                    h2d += b * n * 32; d2h += b * 32
-                elif kind == "axpy":
-                    for i in range(b):
-                        nat.check(L.b200_poly_op(C.c_int(4), nat.ptr(ho[0]), nat.ptr(hc[i]), nat.ptr(xs[i]), nat.ptr(ho[0]), C.c_size_t(n)))
-                    h2d += 2 * b * n * 32; d2h += b * n * 32
-                elif kind == "kate_division":
-                    for i in range(b):
-                        nat.check(L.b200_kate_division(nat.ptr(hc[i]), C.c_size_t(n), nat.ptr(xs[i]), nat.ptr(ho[i][: n - 1])))
-                    h2d += b * n * 32; d2h += b * (n - 1) * 32
-                done += b
-        return h2d, d2h
-
-    class _HostBases:      # adapter: halo2.best_multiexp_batch wants .handle / .n
-        def __init__(self, db):
-            self.handle, self.n = db.handle, db.n
+        for i in my_inputs:
+            nat.check(L.b200_dev_upload(nat.dev(e2e_pool[i % ncols].data_ptr()), C.c_void_p(host_cols[i % ncols].data_ptr()), C.c_size_t(n * 32)))
+            h2d += n * 32
+        pts = step_device(e2e_pool)
+        jac = dev.normalize(pts)                                  # D2H of the XYZZ partials + host normalisation
+        d2h += pts.numel() * 8
+        for e in evals:
+            host_evals[: e.shape[0]].copy_(e)
+            d2h += e.numel() * 8
+        torch.cuda.synchronize()
+        return h2d, d2h, jac
 
     def barrier():
         if world > 1:
@@ -311,12 +339,12 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        h2d, d2h = step_host()
+        h2d, d2h, _ = step_host()
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     clocks = sampler.summary()
 
-    pairs, ntt_elts = count_units(ops, n, tr["ext_bits"])
+    pairs, ntt_elts = count_units(ops, n, tr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -342,8 +370,8 @@ def run_b200(args):
         "metric": "prove_time_s", "value": round(ms_dev / 1e3, 6), "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 limbs (254-bit Montgomery integers mod BN254 r/p)", "data": "synthetic",
-        "config": {"workload": "prove-trace replay, %s-shaped circuit at k=%d (MSM+NTT+poly stages of create_proof; synthesize, transcript and "
-                               "evaluate_h not replayed)" % (tname, k), "k": k, "trace": tr, "msm_pairs_per_step": pairs, "ntt_elts_per_step": ntt_elts,
+        "config": {"workload": "prove-trace replay, %s-shaped circuit at k=%d (MSM, NTT, evaluate_h with a synthetic gate program and poly stages of create_proof; "
+                               "synthesize and transcript stay on the CPU and are not replayed)" % (tname, k), "k": k, "trace": tr, "msm_pairs_per_step": pairs, "ntt_elts_per_step": ntt_elts,
                    "parallelism": "columns round-robin over %d GPU(s)" % world,
                    "l2": "inputs larger than L2: %d MB of columns + %d MB tables per step" % (ncols * n * 32 >> 20, (2 * n * 64 * 17) >> 20)},
         "e2e": {"value": round(ms_e2e / 1e3, 6), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
@@ -393,12 +421,21 @@ def cpu_trace(k, tname, budget_s=20.0, threads=None):
             orc.prefix_scan(col, one, False)
         elif kind == "intt":
             orc.lagrange_to_coeff(col, k, threads)
-        elif kind == "coset_ntt":
+        elif kind == "quotient":
+            # stages 6-7 on the CPU: one coset NTT and one evaluate_h group are timed and scaled by their counts
+            ncoset = n_coset_columns(tr)
+            m = min(ncoset, QUOTIENT_GROUP if ext_k <= 23 else 16)
+            t0 = time.perf_counter()
             ext = orc.coeff_to_extended(col, ext_k, threads)
-        elif kind == "divide_vanishing":
-            orc.divide_by_vanishing(ext if ext is not None else orc.coeff_to_extended(col, ext_k, threads), k, ext_k)
-        elif kind == "ext_intt":
-            orc.extended_to_coeff(ext if ext is not None else orc.coeff_to_extended(col, ext_k, threads), ext_k, threads)
+            t_coset = time.perf_counter() - t0
+            loads, consts, prog = gate_program(m).arrays()
+            t0 = time.perf_counter()
+            hq = orc.quotient_eval([ext] * (m + 1), k, ext_k, loads, consts, prog, threads)
+            t_eval = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            orc.extended_to_coeff(orc.divide_by_vanishing(hq, k, ext_k), ext_k, threads)
+            t_tail = time.perf_counter() - t0
+            return t_coset * ncoset + t_eval * (ncoset / m) + t_tail
         elif kind == "eval":
             orc.eval_polynomial(col, x)
         elif kind == "axpy":
@@ -417,8 +454,8 @@ def cpu_trace(k, tname, budget_s=20.0, threads=None):
     while True:
         for kind in kinds:
             t0 = time.perf_counter()
-            run_one(kind)
-            per.setdefault(kind, []).append(time.perf_counter() - t0)
+            modelled = run_one(kind)
+            per.setdefault(kind, []).append(modelled if modelled is not None else time.perf_counter() - t0)
         reps += 1
         if time.perf_counter() - t_start > budget_s or reps >= 5:
             break
@@ -437,7 +474,7 @@ def run_reference(args):
     tname = args.trace or CONFIG_FOR_K.get(k, "conv2d_mnist")
     tr = TRACES[tname]
     ops = trace_ops(tr)
-    pairs, ntt_elts = count_units(ops, 1 << k, tr["ext_bits"])
+    pairs, ntt_elts = count_units(ops, 1 << k, tr)
     vals = []
     base = None
     for _ in range(args.warmup + args.steps):
@@ -448,8 +485,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "prove_time_s", "value": round(v, 4), "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(v * 1e3, 1), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64 limbs (254-bit Montgomery integers)", "data": "synthetic",
-            "config": {"workload": "prove-trace replay, %s-shaped circuit at k=%d (MSM+NTT+poly stages of create_proof; synthesize, transcript and "
-                                   "evaluate_h not replayed)" % (tname, k), "k": k, "trace": tr, "msm_pairs_per_step": pairs, "ntt_elts_per_step": ntt_elts},
+            "config": {"workload": "prove-trace replay, %s-shaped circuit at k=%d (MSM, NTT, evaluate_h with a synthetic gate program and poly stages of create_proof; "
+                                   "synthesize and transcript stay on the CPU and are not replayed)" % (tname, k), "k": k, "trace": tr, "msm_pairs_per_step": pairs, "ntt_elts_per_step": ntt_elts},
             "cpu_baseline": base,
             "e2e": {"value": round(v, 4), "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
