@@ -310,6 +310,12 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.profile_one_step:          # for `ncu`: setup + exactly one device-resident step, nothing else
+        step_device()
+        torch.cuda.synchronize()
+        print("one step done")
+        return
+
     # ---- device-resident timing
     for _ in range(args.warmup):
         step_device()
@@ -502,6 +508,7 @@ def main():
     ap.add_argument("--trace", default=None, choices=[None] + list(TRACES))
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one-step", action="store_true", help="setup + one device step only (for ncu launch lists)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

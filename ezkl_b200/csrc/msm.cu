@@ -21,7 +21,7 @@
 namespace b200 {
 
 static constexpr int HEAVY_CHUNKS = 32;     // buckets with more chunks than this are summed by a whole block
-static constexpr int REDUCE_M = 8;          // buckets per thread in k_reduce
+static constexpr int REDUCE_M_MAX = 32;      // buckets per thread in k_reduce: 8 for small batches (latency), 32 for large (work)
 static constexpr int TREE_THREADS = 256;
 
 int msm_default_window(size_t n) {
@@ -280,15 +280,15 @@ __global__ void __launch_bounds__(TREE_THREADS) k_combine_heavy(const uint32_t* 
 
 // 10: sum_b (b+1) * B_b.  Thread t owns buckets [t*M, (t+1)*M): running sums give sum_j (j+1) B and S = sum B;
 //     the block offset (t*M) * S is a small scalar multiple; then a block tree.
-__global__ void __launch_bounds__(TREE_THREADS) k_reduce(const G1Xyzz* __restrict__ bucket_sums, uint32_t nbuckets, G1Xyzz* __restrict__ partials, uint32_t nparts) {
+__global__ void __launch_bounds__(TREE_THREADS) k_reduce(const G1Xyzz* __restrict__ bucket_sums, uint32_t nbuckets, G1Xyzz* __restrict__ partials, uint32_t nparts, uint32_t per_thread) {
     __shared__ G1Xyzz sh[TREE_THREADS];
     const uint32_t col = blockIdx.y;
     const G1Xyzz* bs = bucket_sums + (size_t)col * nbuckets;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lo = t * REDUCE_M;
+    const uint32_t lo = t * per_thread;
     G1Xyzz run = g1_xyzz_identity(), acc = g1_xyzz_identity();
     if (lo < nbuckets) {
-        const uint32_t hi = min(lo + (uint32_t)REDUCE_M, nbuckets);
+        const uint32_t hi = min(lo + per_thread, nbuckets);
 #pragma unroll 1
         for (uint32_t b = hi; b-- > lo;) {
             run = g1_add(run, bs[b]);
@@ -376,7 +376,8 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const uint32_t cap = pick_cap(ent_stride * batch);
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
-    const uint32_t nparts = div_up(div_up(nb, REDUCE_M), TREE_THREADS);
+    const uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
+    const uint32_t nparts = div_up(div_up(nb, reduce_m), TREE_THREADS);
 
     // counts region (zeroed every call): hist | cursor | len_hist | len_cursor | heavy
     const size_t n_hist = (size_t)batch * nb, n_len = (size_t)batch * (cap + 1), n_heavy = (size_t)batch * heavy_stride;
@@ -423,7 +424,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     }
     k_combine<<<dim3(div_up(nb, 128), batch), 128, 0, st>>>(chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     k_combine_heavy<<<dim3(32, batch), TREE_THREADS, 0, st>>>(heavy, heavy_stride, chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
-    k_reduce<<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts);
+    k_reduce<<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
     k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
     B200_CUDA(cudaGetLastError());
     return 0;

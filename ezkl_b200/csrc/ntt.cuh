@@ -14,6 +14,8 @@ struct NttPlan {
     int npass = 0;
     int logm[3] = {0, 0, 0};
     Fr* d_tw[3] = {nullptr, nullptr, nullptr};   // per pass: (omega^(N/M))^k, k < M/2
+    uint4* d_staged[3] = {nullptr, nullptr, nullptr};   // per pass: per-stage twiddles, planar (v2 kernel)
+    Fr* d_full = nullptr;     // omega^e, e < N (log_n <= 22): single-multiply inter-pass twiddles
     Fr* d_lo = nullptr;       // omega^e, e < 2^lo_bits
     Fr* d_hi = nullptr;       // omega^(e << lo_bits), e < N >> lo_bits
     uint32_t lo_bits = 0;

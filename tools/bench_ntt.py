@@ -36,15 +36,13 @@ def run(log_n, batch, reps=5):
 
 if __name__ == "__main__":
     nat.init(0)
-    configs = [("default", {}), ("G1 T256", {"B200_NTT_LOGG": "0", "B200_NTT_THREADS": "256"}), ("G1 T512", {"B200_NTT_LOGG": "0", "B200_NTT_THREADS": "512"}),
-               ("G2 T512", {"B200_NTT_LOGG": "1", "B200_NTT_THREADS": "512"}), ("G4 T512", {"B200_NTT_LOGG": "2", "B200_NTT_THREADS": "512"}),
-               ("G2 T256", {"B200_NTT_LOGG": "1", "B200_NTT_THREADS": "256"})]
+    configs = [("v2 default", {}), ("v2 no-full-table", {"B200_NTT_NOFULL": "1"}), ("v1 (radix-2 smem)", {"B200_NTT_V": "1"})]
     if len(sys.argv) > 1:
         configs = [("default", {})]
     for log_n, batch in ((17, 32), (20, 8), (22, 2), (25, 1)):
         for name, env in configs:
-            for kk in ("B200_NTT_LOGG", "B200_NTT_THREADS"):
+            for kk in ("B200_NTT_LOGG", "B200_NTT_THREADS", "B200_NTT_V", "B200_NTT_NOFULL"):
                 os.environ.pop(kk, None)
             os.environ.update(env)
             g, ms = run(log_n, batch)
-            print("log_n=%2d batch=%3d  %-10s %8.3f ms  %7.3f G elts/s  (%5.1f GB/s algorithmic)" % (log_n, batch, name, ms, g, g * 64), flush=True)
+            print("log_n=%2d batch=%3d  %-18s %8.3f ms  %7.3f G elts/s  (%5.1f GB/s algorithmic)" % (log_n, batch, name, ms, g, g * 64), flush=True)
