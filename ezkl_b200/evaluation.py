@@ -199,3 +199,59 @@ def evaluate_h_device(program: QuotientProgram, columns, k: int, ext_k: int, out
                                                C.c_size_t(loads.shape[0]), nat.ptr(consts) if consts.size else None, C.c_size_t(consts.shape[0]),
                                                prog.ctypes.data_as(C.c_void_p), C.c_size_t(prog.shape[0]), nat.dev(out.data_ptr()), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Permutation grand product and mv-lookup grand sum (halo2 plonk/permutation/prover.rs, plonk/mv_lookup/prover.rs; stage 3
+# of create_proof): row-wise numerator / denominator programs on the Lagrange domain (the same
+# interpreter with k == ext_k), one batch inversion, one running product / sum.  All on the device.
+DELTA = pow(7, 1 << 28, F.FR_MODULUS)          # Fr::DELTA = GENERATOR^(2^S): coset separator of the permutation argument
+
+
+def _omega_powers_column(k: int) -> np.ndarray:
+    """Lagrange-domain column of omega^i (the identity polynomial's values), built on the host once per k."""
+    w = pow(F.FR_ROOT_OF_UNITY, 1 << (F.FR_S - k), F.FR_MODULUS)
+    out, cur = [], 1
+    for _ in range(1 << k):
+        out.append(F.fr_to_limbs(cur))
+        cur = cur * w % F.FR_MODULUS
+    return np.stack(out)
+
+
+def permutation_product(values, sigmas, k: int, beta: int, gamma: int, delta_start: int = 1) -> np.ndarray:
+    """z(X) in Lagrange form for one permutation chunk:  z[0] = 1,
+        z[i+1] = z[i] * prod_j (v_j[i] + beta * delta_start * DELTA^j * omega^i + gamma) / (v_j[i] + beta * sigma_j[i] + gamma).
+    values / sigmas: lists of [n,4] Lagrange columns (wire form)."""
+    from . import halo2 as h2
+    m = len(values)
+    assert m == len(sigmas) and m > 0
+    r = F.FR_MODULUS
+    cols = list(values) + list(sigmas) + [_omega_powers_column(k)]
+    X = Query(2 * m)
+    num = den = None
+    for j in range(m):
+        d = delta_start * pow(DELTA, j, r) % r
+        tn = Query(j) + X * Constant(beta * d % r) + Constant(gamma)
+        td = Query(j) + Query(m + j) * Constant(beta) + Constant(gamma)
+        num = tn if num is None else num * tn
+        den = td if den is None else den * td
+    numer = evaluate_h(QuotientProgram(num), cols, k, k)
+    denom = h2.batch_invert(evaluate_h(QuotientProgram(den), cols, k, k))
+    ratio = h2.poly_op("mul", numer, denom)
+    return h2.prefix_scan(ratio, F.fr_to_limbs(1), True)
+
+
+def lookup_grand_sum(inputs, table, multiplicities, k: int, beta: int) -> np.ndarray:
+    """phi(X) in Lagrange form for a logUp / mv-lookup argument:  phi[0] = 0,
+        phi[i+1] = phi[i] + sum_j 1 / (f_j[i] + beta) - m[i] / (t[i] + beta).
+    inputs: list of compressed input-expression columns f_j; table: compressed table column t; multiplicities: m."""
+    from . import halo2 as h2
+    nin = len(inputs)
+    cols = list(inputs) + [table]
+    one = F.fr_to_limbs(1)
+    dens = [h2.batch_invert(evaluate_h(QuotientProgram(Query(j) + Constant(beta)), cols, k, k)) for j in range(nin + 1)]
+    acc = dens[0]
+    for j in range(1, nin):
+        acc = h2.poly_op("add", acc, dens[j])
+    acc = h2.poly_op("sub", acc, h2.poly_op("mul", multiplicities, dens[nin]))
+    return h2.prefix_scan(acc, np.zeros(4, np.uint64), False)

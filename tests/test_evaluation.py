@@ -118,3 +118,60 @@ def test_quotient_pipeline_on_a_satisfied_gate():
     numerator = ((ev_at[4] * ev_at[0] * ev_at[1] + ev_at[5] - ev_at[2]) * y + (a_rot - ev_at[3])) % R
     hx = H.fr_unwire(h2.eval_polynomial(h, xv))
     assert numerator == hx * (pow(x, n, R) - 1) % R
+
+
+@pytest.mark.gpu
+def test_permutation_product_and_lookup_sum():
+    """Grand product z(X) of a real permutation (copy constraints satisfied) closes to 1; logUp grand sum closes to 0;
+    both match a python-int restatement row by row."""
+    from ezkl_b200 import _native as nat
+    nat.init(-1)
+    rng = random.Random(12)
+    k, m = 7, 3
+    n = 1 << k
+    w = pyref.omega_for(k)
+    # a random permutation over the m*n cells, values constant on its cycles => the argument is satisfied
+    cells = [(j, i) for j in range(m) for i in range(n)]
+    perm = cells[:]
+    rng.shuffle(perm)
+    sigma_of = dict(zip(cells, perm))
+    val, seen = {}, set()
+    for c in cells:
+        if c in seen:
+            continue
+        v, cur = rng.randrange(R), c
+        while cur not in seen:
+            seen.add(cur)
+            val[cur] = v
+            cur = sigma_of[cur]
+    label = lambda j, i: pow(ev.DELTA, j, R) * pow(w, i, R) % R
+    values = [[val[(j, i)] for i in range(n)] for j in range(m)]
+    sigmas = [[label(*sigma_of[(j, i)]) for i in range(n)] for j in range(m)]
+    beta, gamma = rng.randrange(R), rng.randrange(R)
+    z = H.fr_list(ev.permutation_product([H.fr_array(v) for v in values], [H.fr_array(s) for s in sigmas], k, beta, gamma))
+    exp, acc = [], 1
+    for i in range(n):
+        exp.append(acc)
+        num = den = 1
+        for j in range(m):
+            num = num * (values[j][i] + beta * label(j, i) + gamma) % R
+            den = den * (values[j][i] + beta * sigmas[j][i] + gamma) % R
+        acc = acc * num * pow(den, -1, R) % R
+    assert z == exp
+    assert acc == 1                      # full product over the domain is 1 for a satisfied permutation
+    # logUp: every input value appears in the table; multiplicities count occurrences
+    table = [rng.randrange(R) for _ in range(n)]
+    ins = [[table[rng.randrange(n)] for _ in range(n)] for _ in range(2)]
+    mult = [0] * n
+    pos = {}
+    for i, t in enumerate(table):
+        pos.setdefault(t, i)
+    for col in ins:
+        for v in col:
+            mult[pos[v]] += 1
+    phi = H.fr_list(ev.lookup_grand_sum([H.fr_array(c) for c in ins], H.fr_array(table), H.fr_array(mult), k, beta))
+    exp, acc = [], 0
+    for i in range(n):
+        exp.append(acc)
+        acc = (acc + sum(pow(c[i] + beta, -1, R) for c in ins) - mult[i] * pow(table[i] + beta, -1, R)) % R
+    assert phi == exp and acc == 0
