@@ -370,6 +370,15 @@ def run_b200(args):
     launch_cols = my_msm_cols * args.steps / max(acc_cnt, 1)
     alg_bytes_per_launch = launch_cols * n * (32.0 + 64.0 / max(launch_cols, 1.0))
     achieved = alg_bytes_per_launch / ((acc_ms / max(acc_cnt, 1)) * 1e-3) / 1e9 if acc_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this same command (k = 17 only)
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_bench_step_k17.json")))["k_accumulate"]
+        if k == 17 and tname == "conv2d_mnist" and world == 1:
+            rd, wr = cap["dram__bytes_read.sum"]["per_launch"], cap["dram__bytes_write.sum"]["per_launch"]
+            traffic = int(sum(rd + wr) * 1e9 / len(rd))
+    except Exception:
+        pass
     msm_ms = prof["msm_total"][0] / args.steps
     ntt_ms = prof["ntt"][0] / args.steps
     line = {
@@ -384,7 +393,7 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "k_accumulate (MSM bucket accumulation)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes_per_launch), "avg_launch_ms": round(acc_ms / max(acc_cnt, 1), 4),
                      "note": "integer-issue bound (254-bit modular arithmetic), not HBM bound: see DESIGN.md"},
         "msm_pairs_per_s": round(pairs / world / (msm_ms * 1e-3), 1) * world if msm_ms > 0 else None,
