@@ -231,6 +231,22 @@ class EvaluationDomain:
         nat.check(nat.lib().b200_poly_scale_cycle(nat.ptr(a), C.c_size_t(a.shape[0]), nat.ptr(self.t_evaluations), C.c_uint32(self.t_evaluations.shape[0])))
         return a
 
+    def keygen_l_polys(self, blinding_factors: int):
+        """l0, l_last, l_active_row on the extended coset, as halo2 keygen_pk builds them (UPSTREAM plonk/keygen.rs; entered
+        from /root/reference/src/pfsys/mod.rs:396): l0 = L_0, l_last = L_{n - blinding_factors - 1},
+        l_active_row = 1 - (l_last + l_blind) with l_blind = sum of the Lagrange polynomials of the last blinding rows."""
+        n = self.n
+        one = F.fr_to_limbs(1)
+        rows = np.zeros((3, n, 4), np.uint64)
+        rows[0, 0] = one
+        rows[1, n - blinding_factors - 1] = one
+        rows[2, n - blinding_factors:] = one
+        coeffs = self.lagrange_to_coeff_batch([rows[0], rows[1], rows[2]])
+        l0, l_last, l_blind = self.coeff_to_extended_batch(coeffs)
+        ones = np.tile(one, (self.extended_len(), 1))
+        l_active = poly_op("sub", ones, poly_op("add", l_last, l_blind))
+        return l0, l_last, l_active
+
     def rotate_omega(self, value: int, rotation: int) -> int:
         r = F.FR_MODULUS
         return value * pow(self._omega, rotation % self.n, r) % r
@@ -286,3 +302,72 @@ class ParamsKZG:
 
     def commit_batch(self, polys) -> np.ndarray:
         return best_multiexp_batch(polys, self._get("g"))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# plonk/keygen.rs + plonk.rs ProvingKey (RawBytes layout)
+class ProvingKey:
+    """ProvingKey<G1Affine> as `ProvingKey::write(.., SerdeFormat::RawBytes)` lays it out (what src/pfsys/mod.rs:615-636 loads):
+    vk bytes | l0 | l_last | l_active_row | fixed_values | fixed_polys | fixed_cosets | permutations | polys | cosets.
+    The constraint system is not in the file (upstream re-derives it from the circuit), so the two counts the layout depends on
+    are arguments.  `keygen_pk_polys` recomputes every derived vector on the device from fixed_values / permutations."""
+
+    def __init__(self):
+        self.k = 0
+        self.vk_bytes = b""
+        self.l0 = self.l_last = self.l_active_row = None
+        self.fixed_values, self.fixed_polys, self.fixed_cosets = [], [], []
+        self.permutations, self.permutation_polys, self.permutation_cosets = [], [], []
+
+    @staticmethod
+    def _poly(d, off):
+        (ln,) = struct.unpack(">I", d[off:off + 4])
+        off += 4
+        return np.frombuffer(d, dtype="<u8", count=4 * ln, offset=off).reshape(ln, 4).copy(), off + 32 * ln
+
+    @classmethod
+    def _slice(cls, d, off):
+        (cnt,) = struct.unpack(">I", d[off:off + 4])
+        off += 4 + 4 * cnt                       # parallel-poly-read length table
+        out = []
+        for _ in range(cnt):
+            p, off = cls._poly(d, off)
+            out.append(p)
+        return out, off
+
+    @classmethod
+    def read(cls, path: str, num_permutation_columns: int, num_selectors: int) -> "ProvingKey":
+        d = open(path, "rb").read()
+        pk = cls()
+        ver, k = d[0], d[1]
+        if ver != 3:
+            raise nat.B200Error("ProvingKey::read: unsupported key version %d" % ver)
+        pk.k = k
+        (nf,) = struct.unpack("<I", d[3:7])
+        off = 7 + 64 * nf + 64 * num_permutation_columns + num_selectors * ((1 << k) // 8)
+        pk.vk_bytes = d[:off]
+        try:
+            pk.l0, off = cls._poly(d, off)
+            pk.l_last, off = cls._poly(d, off)
+            pk.l_active_row, off = cls._poly(d, off)
+            pk.fixed_values, off = cls._slice(d, off)
+            pk.fixed_polys, off = cls._slice(d, off)
+            pk.fixed_cosets, off = cls._slice(d, off)
+            pk.permutations, off = cls._slice(d, off)
+            pk.permutation_polys, off = cls._slice(d, off)
+            pk.permutation_cosets, off = cls._slice(d, off)
+        except (ValueError, struct.error) as e:
+            raise nat.B200Error("ProvingKey::read: malformed key or wrong column counts (%s)" % e)
+        if off != len(d):
+            raise nat.B200Error("ProvingKey::read: %d trailing bytes (wrong column counts?)" % (len(d) - off))
+        return pk
+
+    def keygen_pk_polys(self, j: int, blinding_factors: int):
+        """Recompute on the device what keygen_pk derives (create_keys, /root/reference/src/pfsys/mod.rs:376-400):
+        fixed_polys / cosets, permutation polys / cosets, l0 / l_last / l_active_row.  Returns a dict of lists."""
+        dom = EvaluationDomain(j, self.k)
+        fp = dom.lagrange_to_coeff_batch(self.fixed_values)
+        pp = dom.lagrange_to_coeff_batch(self.permutations)
+        l0, l_last, l_active = dom.keygen_l_polys(blinding_factors)
+        return {"fixed_polys": fp, "fixed_cosets": dom.coeff_to_extended_batch(fp), "permutation_polys": pp,
+                "permutation_cosets": dom.coeff_to_extended_batch(pp), "l0": l0, "l_last": l_last, "l_active_row": l_active}

@@ -384,3 +384,24 @@ def test_msm_k22_vs_oracle():
     bases = h2.Bases(bases_np)
     assert np.array_equal(jac_to_affine(h2.best_multiexp(sc, bases))[0], orc.msm(sc, bases_np, THREADS))
     bases.release()
+
+
+def test_keygen_pk_reproduces_reference_proving_key_bytes(tmp_path):
+    """create_keys (src/pfsys/mod.rs:376-400): from the fixture's fixed_values / permutations alone, the device keygen
+    transforms must reproduce the reference pk.key's derived vectors byte for byte (polys, extended cosets, l0, l_last,
+    l_active_row), for the columns carried in tests/golden/pk_k6_subset.npz."""
+    pk = H.load_pk_fixture()
+    key = h2.ProvingKey()
+    key.k = 6
+    cols = (0, 1, 5, 37)
+    key.fixed_values = [pk["fixed_values_%d" % c] for c in cols]
+    key.permutations = [pk["perm_values_0"]]
+    out = key.keygen_pk_polys(9, 5)
+    for i, c in enumerate(cols):
+        assert np.array_equal(out["fixed_polys"][i], pk["fixed_polys_%d" % c])
+        assert np.array_equal(out["fixed_cosets"][i], pk["fixed_cosets_%d" % c])
+    assert np.array_equal(out["permutation_polys"][0], pk["perm_polys_0"])
+    assert np.array_equal(out["permutation_cosets"][0], pk["perm_cosets_0"])
+    assert np.array_equal(out["l0"], pk["l0"])
+    assert np.array_equal(out["l_last"], pk["l_last"])
+    assert np.array_equal(out["l_active_row"], pk["l_active_row"])

@@ -115,3 +115,22 @@ def test_signed_window_recoding(c):
     for i, x in enumerate(xs):
         assert sum(int(out[i, w]) << (c * w) for w in range(W)) == x
         assert all(-(1 << (c - 1)) <= int(d) <= (1 << (c - 1)) for d in out[i])
+
+
+def test_proving_key_reader_on_reference_fixture():
+    """ProvingKey::read mirror against the reference's own tests/assets/pk.key (present in the build container only)."""
+    path = "/root/reference/tests/assets/pk.key"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present (GPU box)")
+    from ezkl_b200 import halo2 as h2
+    pk = h2.ProvingKey.read(path, num_permutation_columns=32, num_selectors=80)
+    g = H.load_pk_fixture()
+    assert pk.k == 6 and len(pk.fixed_values) == 38 and len(pk.permutations) == 32
+    assert pk.l0.shape == (512, 4) and pk.fixed_cosets[0].shape == (512, 4) and pk.fixed_polys[0].shape == (64, 4)
+    for c in (0, 1, 5, 37):
+        assert np.array_equal(pk.fixed_values[c], g["fixed_values_%d" % c])
+        assert np.array_equal(pk.fixed_polys[c], g["fixed_polys_%d" % c])
+        assert np.array_equal(pk.fixed_cosets[c], g["fixed_cosets_%d" % c])
+    assert np.array_equal(pk.permutation_cosets[0], g["perm_cosets_0"]) and np.array_equal(pk.l_active_row, g["l_active_row"])
+    with pytest.raises(nat.B200Error):
+        h2.ProvingKey.read(path, num_permutation_columns=31, num_selectors=80)      # wrong layout is detected, not mis-parsed
