@@ -60,7 +60,7 @@ def trace_ops(tr):
         ("quotient", 1),                            # stages 6-7: ncoset coset NTTs -> evaluate_h -> divide by vanishing -> extended iNTT
         ("msm_coeff", Q),
         ("eval", tr["evals"]),                      # stage 8
-        ("axpy", npolys),                           # stage 9: SHPLONK linear combinations
+        ("lincomb", tr["shplonk_sets"]),            # stage 9: SHPLONK linear combinations (npolys polynomials over the rotation sets)
         ("kate_division", tr["shplonk_sets"]),
         ("msm_coeff", 2),
     ]
@@ -227,6 +227,8 @@ def run_b200(args):
     commits = []
 
     evals = []
+    npolys_total = tr["advice"] + tr["fixed"] + tr["perm_cols"] + tr["perm_z"] + 2 * tr["lookups"] + 1 + tr["quotient_pieces"]
+    lin_scalars = np.ascontiguousarray(np.tile(xs, (npolys_total // ncols + 1, 1))[:npolys_total])
 
     def step_device(pool=None):
         """One proof's trace with device-resident columns (pool defaults to the resident synthetic columns)."""
@@ -260,9 +262,10 @@ def run_b200(args):
                     quotient_stage(lambda j: cols_[j % ncols], None)
                 elif kind == "eval":
                     evals.append(dev.eval_batch(v, xs[:b]))
-                elif kind == "axpy":
+                elif kind == "lincomb":
+                    per_set = max(1, npolys_total // tr["shplonk_sets"])
                     for i in range(b):
-                        dev.poly_op("axpy", out_n[0], v[i], s=xs[i], out=out_n[0])
+                        dev.lincomb([cols_[j % ncols] for j in range(per_set)], lin_scalars[:per_set], out=out_n[i])
                 elif kind == "kate_division":
                     for i in range(b):
                         dev.kate_division(v[i], xs[i], out=out_n[i][: n - 1])
@@ -457,8 +460,11 @@ def cpu_trace(k, tname, budget_s=20.0, threads=None):
             return t_coset * ncoset + t_eval * (ncoset / m) + t_tail
         elif kind == "eval":
             orc.eval_polynomial(col, x)
-        elif kind == "axpy":
+        elif kind == "lincomb":
+            per_set = max(1, (tr["advice"] + tr["fixed"] + tr["perm_cols"] + tr["perm_z"] + 2 * tr["lookups"] + 1 + tr["quotient_pieces"]) // tr["shplonk_sets"])
+            t0 = time.perf_counter()
             orc.poly_op("axpy", col, col, x, threads=threads)
+            return (time.perf_counter() - t0) * per_set
         elif kind == "kate_division":
             orc.kate_division(col, x)
 

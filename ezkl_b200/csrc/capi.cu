@@ -415,6 +415,31 @@ int b200_poly_op(int op, const b200_fr* a, const b200_fr* b, const b200_fr* s, b
     B200_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
+int b200_poly_lincomb_dev(const void* const* d_polys, const b200_fr* scalars, size_t count, size_t n, void* d_out, void* stream) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(d_out && (count == 0 || (d_polys && scalars)), -1, "poly_lincomb: null pointer");
+    std::vector<Fr> sv(count);
+    if (count) memcpy(sv.data(), scalars, sizeof(Fr) * count);
+    int rc = poly_lincomb(reinterpret_cast<const Fr* const*>(d_polys), sv.data(), count, reinterpret_cast<Fr*>(d_out), n, c->poly_ws, pick_stream(c, stream));
+    if (!rc && n) g_launches += 1;
+    return rc;
+}
+int b200_poly_lincomb(const b200_fr* const* polys, const b200_fr* scalars, size_t count, size_t n, b200_fr* out) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(out && (count == 0 || (polys && scalars)), -1, "poly_lincomb: null pointer");
+    if (n == 0) return 0;
+    if (c->stage_a.ensure(sizeof(Fr) * n * (count ? count : 1)) || c->stage_b.ensure(sizeof(Fr) * n)) return -2;
+    std::vector<const void*> ptrs(count);
+    for (size_t j = 0; j < count; ++j) {
+        B200_CHECK(polys[j], -1, "poly_lincomb: polys[%zu] is null", j);
+        ptrs[j] = c->stage_a.as<Fr>() + j * n;
+        B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + j * n, polys[j], sizeof(Fr) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (int rc = b200_poly_lincomb_dev(ptrs.data(), scalars, count, n, c->stage_b.p, nullptr)) return rc;
+    B200_CUDA(cudaMemcpyAsync(out, c->stage_b.p, sizeof(Fr) * n, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
 int b200_poly_scale_cycle_dev(void* d_a, size_t n, const b200_fr* consts, uint32_t period, void* stream) {
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(d_a && consts && period > 0 && period <= 1024, -1, "poly_scale_cycle: bad argument");

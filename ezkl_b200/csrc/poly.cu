@@ -6,6 +6,7 @@
 //   columns (create_proof stages 2-9; entered from /root/reference/src/pfsys/mod.rs:456).
 // The element-wise kernels are HBM-bound (96 / 64 B per element); scans and evaluation are chunked so that each
 // thread does a serial run of CHUNK elements and only O(n / CHUNK) values go through the block/grid combine steps.
+#include <cstring>
 #include <vector>
 #include "poly.cuh"
 
@@ -31,12 +32,36 @@ __global__ void __launch_bounds__(256) k_poly_scale_cycle(const Fr* __restrict__
         fp_store(out + i, fp_load(a + i) * fp_load(consts + (i % period)));
 }
 
+// out[i] = sum_j scalars[j] * polys[j][i]   (one pass: each polynomial is read once, the sum lives in registers)
+__global__ void __launch_bounds__(256) k_poly_lincomb(const Fr* const* __restrict__ polys, const Fr* __restrict__ scalars, uint32_t count, Fr* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        Fr acc = fp_zero<FrTag>();
+#pragma unroll 1
+        for (uint32_t j = 0; j < count; ++j) acc = acc + fp_load(scalars + j) * fp_load(polys[j] + i);
+        fp_store(out + i, acc);
+    }
+}
+
 static unsigned ew_grid(size_t n) { unsigned g = div_up(n, 256); return g > 148u * 16u ? 148u * 16u : (g ? g : 1); }
 
 int poly_binary(int op, const Fr* a, const Fr* b, const Fr* h_s, Fr* out, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     Fr s = h_s ? *h_s : fp_zero<FrTag>();
     k_poly_binary<<<ew_grid(n), 256, 0, st>>>(op, a, b, s, out, n);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+int poly_lincomb(const Fr* const* h_polys /*device addresses*/, const Fr* h_scalars, size_t count, Fr* out, size_t n, PolyWorkspace& ws, cudaStream_t st) {
+    if (n == 0) return 0;
+    B200_CHECK(count < (1u << 24), -1, "poly_lincomb: too many terms");
+    const size_t o_s = (sizeof(void*) * count + 31) & ~(size_t)31, total = o_s + sizeof(Fr) * count + 32;
+    std::vector<uint8_t> blob(total, 0);
+    if (count) { memcpy(blob.data(), h_polys, sizeof(void*) * count); memcpy(blob.data() + o_s, h_scalars, sizeof(Fr) * count); }
+    if (ws.scratch.ensure(total)) return -2;
+    B200_CUDA(cudaMemcpyAsync(ws.scratch.p, blob.data(), total, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    uint8_t* d = ws.scratch.as<uint8_t>();
+    k_poly_lincomb<<<ew_grid(n), 256, 0, st>>>(reinterpret_cast<const Fr* const*>(d), reinterpret_cast<const Fr*>(d + o_s), (uint32_t)count, out, n);
     B200_CUDA(cudaGetLastError());
     return 0;
 }
@@ -112,7 +137,8 @@ __global__ void __launch_bounds__(1024) k_wscan_carries(const Fr* __restrict__ b
     const uint32_t lo = threadIdx.x * ipt, hi = min(lo + ipt, nblk);
     Fr v = fp_zero<FrTag>();
     for (uint32_t u = hi; u-- > lo && hi > lo;) v = v * w.xt + fp_load(val + u);
-    Fr step = fp_pow_u64(w.xt, (uint64_t)ipt);
+    Fr step = w.xt;                                       // xt^ipt (ipt is 1 unless there are more than 1024 block values)
+    for (uint32_t e = 1; e < ipt; ++e) step = step * w.xt;
     Fr incl = block_weighted_suffix(v, step, sh);      // value of blocks >= lo, relative to block lo
     if (threadIdx.x == 0 && total) fp_store(total + blockIdx.x, incl);
     if (carry && lo < nblk) {
@@ -145,6 +171,8 @@ __global__ void __launch_bounds__(TB) k_wscan_apply(const Fr* __restrict__ a, si
     }
 }
 
+static unsigned carry_threads(uint32_t nblk) { unsigned t = 32; while (t < nblk && t < 1024) t <<= 1; return t; }
+
 static int upload_wargs(const Fr* h_x, int batch, PolyWorkspace& ws, size_t extra_bytes, WArgs** d_w, uint8_t** d_extra, cudaStream_t st) {
     const size_t wbytes = sizeof(WArgs) * batch;
     if (ws.scratch.ensure(wbytes + 256 + extra_bytes)) return -2;
@@ -165,7 +193,7 @@ int poly_eval(const Fr* coeffs, size_t stride, size_t n, const Fr* h_x, Fr* d_ou
     if (int rc = upload_wargs(h_x, batch, ws, sizeof(Fr) * (size_t)nblk * batch, &d_w, &extra, st)) return rc;
     Fr* blk_val = reinterpret_cast<Fr*>(extra);
     k_wscan_block_values<<<dim3(nblk, batch), TB, 0, st>>>(coeffs, stride, n, d_w, blk_val, nblk);
-    k_wscan_carries<<<batch, 1024, 0, st>>>(blk_val, nblk, d_w, nullptr, d_out);
+    k_wscan_carries<<<batch, carry_threads(nblk), 0, st>>>(blk_val, nblk, d_w, nullptr, d_out);
     B200_CUDA(cudaGetLastError());
     return 0;
 }
@@ -180,7 +208,7 @@ int poly_kate_division(const Fr* a, size_t n, const Fr* h_b, Fr* q, PolyWorkspac
     Fr* blk_val = reinterpret_cast<Fr*>(extra);
     Fr* carry = blk_val + nblk;
     k_wscan_block_values<<<dim3(nblk, 1), TB, 0, st>>>(a + 1, 0, m, d_w, blk_val, nblk);
-    k_wscan_carries<<<1, 1024, 0, st>>>(blk_val, nblk, d_w, carry, nullptr);
+    k_wscan_carries<<<1, carry_threads(nblk), 0, st>>>(blk_val, nblk, d_w, carry, nullptr);
     k_wscan_apply<<<nblk, TB, 0, st>>>(a + 1, m, d_w, carry, q);
     B200_CUDA(cudaGetLastError());
     return 0;

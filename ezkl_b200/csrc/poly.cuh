@@ -11,6 +11,8 @@ struct PolyWorkspace { DevBuf scratch; };
 
 // out[i] = a[i] (+|-|*) b[i]  |  a[i]*s  |  a[i] + s*b[i]        (all device pointers; out may alias a or b)
 int poly_binary(int op, const Fr* a, const Fr* b, const Fr* h_s, Fr* out, size_t n, cudaStream_t st);   // h_s: host scalar
+// out[i] = sum_j scalars[j] * polys[j][i]; h_polys = host array of device addresses, h_scalars = host scalars
+int poly_lincomb(const Fr* const* h_polys, const Fr* h_scalars, size_t count, Fr* out, size_t n, PolyWorkspace& ws, cudaStream_t st);
 // out[i] = a[i] * consts[i mod period]   (distribute_powers_zeta: period 3; divide_by_vanishing_poly: period 2^(ext_k-k))
 int poly_scale_cycle(const Fr* a, const Fr* d_consts, uint32_t period, Fr* out, size_t n, cudaStream_t st);
 // out[p] = sum_i coeffs[p*stride + i] * x[p]^i   for p < batch (eval_polynomial); h_x host array, d_out device array

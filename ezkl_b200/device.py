@@ -138,6 +138,21 @@ def poly_op(op: str, a: torch.Tensor, b: torch.Tensor | None = None, s=None, out
     return out
 
 
+def lincomb(polys, scalars, out: torch.Tensor | None = None) -> torch.Tensor:
+    """sum_j scalars[j] * polys[j]; polys = list of [n,4] CUDA tensors (or a [count,n,4] tensor), scalars host [count,4]."""
+    plist = [polys[i] for i in range(len(polys))]
+    for p_ in plist:
+        _chk(p_, 4)
+    n = plist[0].numel() // 4
+    sc = nat.as_u64(scalars, 4)
+    assert sc.shape[0] == len(plist)
+    if out is None:
+        out = torch.empty_like(plist[0])
+    ptrs = (C.c_void_p * len(plist))(*[p_.data_ptr() for p_ in plist])
+    nat.check(nat.lib().b200_poly_lincomb_dev(ptrs, nat.ptr(sc), C.c_size_t(len(plist)), C.c_size_t(n), nat.dev(out.data_ptr()), _stream()))
+    return out
+
+
 def scale_cycle(a: torch.Tensor, consts) -> torch.Tensor:
     _chk(a, 4)
     cs = nat.as_u64(consts, 4)

@@ -151,6 +151,17 @@ def poly_op(op: str, a, b=None, s=None) -> np.ndarray:
     return out
 
 
+def poly_lincomb(polys, scalars) -> np.ndarray:
+    """sum_j scalars[j] * polys[j] in one pass (the multiopen / SHPLONK combinations q(X) = sum y^j p_j(X))."""
+    ps = [_fr(p) for p in polys]
+    sc = _fr(scalars)
+    assert sc.shape[0] == len(ps) and len(ps) > 0
+    out = np.zeros_like(ps[0])
+    nat.ensure_init()
+    nat.check(nat.lib().b200_poly_lincomb(nat.ptr_array(ps), nat.ptr(sc), C.c_size_t(len(ps)), C.c_size_t(ps[0].shape[0]), nat.ptr(out)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 # poly/domain.rs
 class EvaluationDomain:

@@ -93,6 +93,10 @@ int b200_ntt_dev(const void* d_src, size_t src_stride, size_t n_in, void* d_tmp,
  * op: 0 add, 1 sub, 2 mul (element-wise), 3 scale (out = a * s), 4 axpy (out = a + s * b).  out may alias a or b. */
 int b200_poly_op(int op, const b200_fr* a, const b200_fr* b, const b200_fr* s, b200_fr* out, size_t n);
 int b200_poly_op_dev(int op, const void* d_a, const void* d_b, const b200_fr* s, void* d_out, size_t n, void* stream);
+/* out = sum_j scalars[j] * polys[j]  (n coefficients each): the SHPLONK / multiopen linear combinations q(X) = sum y^j p_j(X),
+ * one pass over the inputs instead of count axpy calls */
+int b200_poly_lincomb(const b200_fr* const* polys, const b200_fr* scalars, size_t count, size_t n, b200_fr* out);
+int b200_poly_lincomb_dev(const void* const* d_polys, const b200_fr* scalars, size_t count, size_t n, void* d_out, void* stream);
 /* a[i] *= consts[i mod period]: distribute_powers_zeta (period 3) / divide_by_vanishing_poly (period 2^(ext_k-k)) */
 int b200_poly_scale_cycle(b200_fr* a, size_t n, const b200_fr* consts, uint32_t period);
 int b200_poly_scale_cycle_dev(void* d_a, size_t n, const b200_fr* consts, uint32_t period, void* stream);

@@ -405,3 +405,13 @@ def test_keygen_pk_reproduces_reference_proving_key_bytes(tmp_path):
     assert np.array_equal(out["l0"], pk["l0"])
     assert np.array_equal(out["l_last"], pk["l_last"])
     assert np.array_equal(out["l_active_row"], pk["l_active_row"])
+
+
+def test_poly_lincomb_vs_oracle():
+    n = 5000
+    polys = [orc.gen_scalars(n, seed=200 + i) for i in range(7)]
+    sc = orc.gen_scalars(7, seed=300)
+    exp = np.zeros((n, 4), np.uint64)
+    for p, s_ in zip(polys, sc):
+        exp = orc.poly_op("axpy", exp, p, s_)
+    assert np.array_equal(h2.poly_lincomb(polys, sc), exp)
