@@ -415,3 +415,64 @@ def test_poly_lincomb_vs_oracle():
     for p, s_ in zip(polys, sc):
         exp = orc.poly_op("axpy", exp, p, s_)
     assert np.array_equal(h2.poly_lincomb(polys, sc), exp)
+
+
+def test_msm_randomised_shapes_and_distributions():
+    """Fuzz-style sweep: window bits 4..18, ragged n, small batches, and the scalar distributions ezkl produces
+    (uniform, tiny quantised values, sparse, one dominant value => one giant bucket) — all against the oracle."""
+    rng = random.Random(2024)
+    for case in range(36):
+        n = rng.choice([1, 2, 3, 31, 32, 33, 100, 257, 1000, 2048, 4099])
+        c = rng.choice([0, 4, 5, 7, 9, 12, 15, 18])
+        batch = rng.choice([1, 2, 5])
+        bases_np = orc.gen_bases(n, seed=1000 + case)
+        if case % 5 == 0 and n > 3:
+            bases_np[rng.randrange(n)] = 0                       # an identity base
+            bases_np[1] = bases_np[0]                            # a repeated base
+        cols = []
+        for b in range(batch):
+            kind = rng.choice(["uniform", "small", "sparse", "dominant", "boundary"])
+            if kind == "uniform":
+                xs = [rng.randrange(pyref.R) for _ in range(n)]
+            elif kind == "small":
+                xs = [rng.randrange(1 << rng.choice([1, 8, 20])) for _ in range(n)]
+            elif kind == "sparse":
+                xs = [rng.randrange(pyref.R) if rng.random() < 0.1 else 0 for _ in range(n)]
+            elif kind == "dominant":
+                v = rng.randrange(pyref.R)
+                xs = [v if rng.random() < 0.9 else rng.randrange(pyref.R) for _ in range(n)]
+            else:
+                xs = [rng.choice([pyref.R - 1, pyref.R - 2, 1 << 253, (1 << 128) - 1, 1]) for _ in range(n)]
+            cols.append(H.fr_array(xs))
+        bases = h2.Bases(bases_np, window_bits=c)
+        got = jac_to_affine(h2.best_multiexp_batch(cols, bases))
+        for b in range(batch):
+            assert np.array_equal(got[b], orc.msm(cols[b], bases_np, THREADS)), (case, n, c, b)
+        bases.release()
+
+
+def test_kzg_open_identity_with_known_trapdoor():
+    """End-to-end composition of the GPU primitives as a KZG opening: with an SRS g[i] = s^i * G whose trapdoor s we know,
+    commit(p) - p(x) * G == (s - x) * commit(q) for q = kate_division(p, x) — checked with the oracle's group law, no pairing."""
+    rng = random.Random(77)
+    k = 9
+    n = 1 << k
+    s = rng.randrange(pyref.R)
+    G = np.array(list(H.fq_wire(1)) + list(H.fq_wire(2)), np.uint64)
+    powers, cur = [], 1
+    for _ in range(n):
+        powers.append(cur)
+        cur = cur * s % pyref.R
+    g = orc.g1_scalar_mul(np.tile(G, (n, 1)), H.fr_array(powers))
+    bases = h2.Bases(g)
+    p = orc.gen_scalars(n, seed=5)
+    x = rng.randrange(pyref.R)
+    xv = H.fr_wire(x)
+    q = h2.kate_division(p, xv)
+    px = H.fr_unwire(h2.eval_polynomial(p, xv))
+    cp = jac_to_affine(h2.best_multiexp(p, bases))
+    cq = jac_to_affine(h2.best_multiexp(q, bases))
+    lhs = orc.g1_add_affine(cp, orc.g1_scalar_mul(G.reshape(1, 8), H.fr_array([(-px) % pyref.R])))
+    rhs = orc.g1_scalar_mul(cq, H.fr_array([(s - x) % pyref.R]))
+    assert np.array_equal(lhs, rhs)
+    bases.release()

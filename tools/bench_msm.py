@@ -22,8 +22,34 @@ def run(bases, sc, reps=3):
     return e0.elapsed_time(e1) / reps
 
 
+def sweep():
+    """BASELINE configs[3]: standalone MSM sweep 2^16 .. 2^26 on one GPU (default window), batch 1 and 4."""
+    import json
+    res = []
+    for k in range(16, 27, 2):
+        n = 1 << k
+        pts = dev.generate_bases(n, seed=3)
+        bases = dev.DeviceBases(pts)
+        del pts
+        torch.cuda.empty_cache()
+        for batch in (1, 4):
+            if k >= 26 and batch > 1:
+                continue
+            sc = dev.random_scalars(n, batch=batch, seed=5)
+            ms = run(bases, sc, reps=2 if k >= 24 else 3)
+            res.append({"k": k, "batch": batch, "ms": round(ms, 3), "pairs_per_s": round(batch * n / ms * 1e3, 1), "hbm_frac": round(batch * n * (32 + 64 / batch) / (ms * 1e-3) / 6486.1e9, 5)})
+            print(res[-1], flush=True)
+            del sc
+        bases.release()
+        torch.cuda.empty_cache()
+    print(json.dumps(res))
+
+
 if __name__ == "__main__":
     nat.init(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+        sweep()
+        sys.exit(0)
     ks = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "17,20").split(",")]
     for k in ks:
         n = 1 << k
