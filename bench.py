@@ -225,6 +225,13 @@ def run_b200(args):
                 put_h(coeff[0, : tr["quotient_pieces"] * n])
 
     commits = []
+    commit_counts = [0] * world
+    _g = 0
+    for _kind, _count in ops:
+        if _kind.startswith("msm"):
+            for _i in range(_count):
+                commit_counts[par.column_owner(_g + _i, world)] += 1
+        _g += _count
 
     evals = []
     npolys_total = tr["advice"] + tr["fixed"] + tr["perm_cols"] + tr["perm_z"] + 2 * tr["lookups"] + 1 + tr["quotient_pieces"]
@@ -272,10 +279,7 @@ def run_b200(args):
                 done += b
         pts = torch.cat(commits) if commits else torch.zeros((0, 16), dtype=torch.int64, device="cuda")
         if world > 1:
-            cnt = torch.tensor([pts.shape[0]], device="cuda")
-            cnts = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(cnts, cnt)
-            par.allgather_columns(pts, [int(c.item()) for c in cnts])
+            par.allgather_columns(pts, commit_counts)      # per-rank counts follow from the deal: no size exchange, no host sync
         return pts
 
     L = nat.lib()

@@ -39,6 +39,7 @@ struct Ctx {
     MsmWorkspace msm_ws;
     PolyWorkspace poly_ws;
     QuotientWorkspace quot_ws;
+    StagingRing ring;
     DevBuf stage_a, stage_b, stage_c, small;
     bool ok = false;
 };
@@ -444,9 +445,13 @@ int b200_poly_scale_cycle_dev(void* d_a, size_t n, const b200_fr* consts, uint32
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(d_a && consts && period > 0 && period <= 1024, -1, "poly_scale_cycle: bad argument");
     cudaStream_t st = pick_stream(c, stream);
-    if (c->small.ensure(sizeof(Fr) * period)) return -2;
-    B200_CUDA(cudaMemcpyAsync(c->small.p, consts, sizeof(Fr) * period, cudaMemcpyHostToDevice, st));
-    int rc = poly_scale_cycle(reinterpret_cast<const Fr*>(d_a), c->small.as<Fr>(), period, reinterpret_cast<Fr*>(d_a), n, st);
+    const Fr* d_consts = reinterpret_cast<const Fr*>(c->ring.push(consts, sizeof(Fr) * period, st));
+    if (!d_consts) {
+        if (c->small.ensure(sizeof(Fr) * period)) return -2;
+        B200_CUDA(cudaMemcpyAsync(c->small.p, consts, sizeof(Fr) * period, cudaMemcpyHostToDevice, st));
+        d_consts = c->small.as<Fr>();
+    }
+    int rc = poly_scale_cycle(reinterpret_cast<const Fr*>(d_a), d_consts, period, reinterpret_cast<Fr*>(d_a), n, st);
     if (!rc && n) g_launches += 1;
     return rc;
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 
 namespace b200 {
@@ -41,6 +42,31 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// Small host->device parameter blobs (programs, pointer tables, per-call constants) without a stream synchronisation:
+// the blob is copied into a pinned ring and an async H2D copy into the matching slot of a device ring is enqueued on the
+// caller's stream.  Slots are only reused after a full lap, and a lap boundary synchronises the device, so neither the
+// pinned source nor the device copy can be overwritten while a kernel may still read it.
+struct StagingRing {
+    uint8_t* h = nullptr;
+    uint8_t* d = nullptr;
+    size_t cap = 0, head = 0;
+    void* push(const void* src, size_t bytes, cudaStream_t st) {
+        if (!h) {
+            const size_t want = (size_t)8 << 20;
+            if (cudaMallocHost((void**)&h, want) != cudaSuccess || cudaMalloc((void**)&d, want) != cudaSuccess) { cudaGetLastError(); h = nullptr; return nullptr; }
+            cap = want;
+        }
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        if (need > cap / 4) return nullptr;                       // caller falls back to its synchronous path
+        if (head + need > cap) { if (cudaDeviceSynchronize() != cudaSuccess) return nullptr; head = 0; }
+        memcpy(h + head, src, bytes);
+        if (cudaMemcpyAsync(d + head, h + head, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+        void* out = d + head;
+        head += need;
+        return out;
+    }
 };
 
 // Optional device-side timing of kernel classes with CUDA events on the launching stream (bench.py's roofline leg).

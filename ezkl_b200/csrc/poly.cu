@@ -57,10 +57,13 @@ int poly_lincomb(const Fr* const* h_polys /*device addresses*/, const Fr* h_scal
     const size_t o_s = (sizeof(void*) * count + 31) & ~(size_t)31, total = o_s + sizeof(Fr) * count + 32;
     std::vector<uint8_t> blob(total, 0);
     if (count) { memcpy(blob.data(), h_polys, sizeof(void*) * count); memcpy(blob.data() + o_s, h_scalars, sizeof(Fr) * count); }
-    if (ws.scratch.ensure(total)) return -2;
-    B200_CUDA(cudaMemcpyAsync(ws.scratch.p, blob.data(), total, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaStreamSynchronize(st));
-    uint8_t* d = ws.scratch.as<uint8_t>();
+    uint8_t* d = reinterpret_cast<uint8_t*>(ws.ring.push(blob.data(), total, st));
+    if (!d) {
+        if (ws.scratch.ensure(total)) return -2;
+        B200_CUDA(cudaMemcpyAsync(ws.scratch.p, blob.data(), total, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        d = ws.scratch.as<uint8_t>();
+    }
     k_poly_lincomb<<<ew_grid(n), 256, 0, st>>>(reinterpret_cast<const Fr* const*>(d), reinterpret_cast<const Fr*>(d + o_s), (uint32_t)count, out, n);
     B200_CUDA(cudaGetLastError());
     return 0;
@@ -175,13 +178,16 @@ static unsigned carry_threads(uint32_t nblk) { unsigned t = 32; while (t < nblk 
 
 static int upload_wargs(const Fr* h_x, int batch, PolyWorkspace& ws, size_t extra_bytes, WArgs** d_w, uint8_t** d_extra, cudaStream_t st) {
     const size_t wbytes = sizeof(WArgs) * batch;
-    if (ws.scratch.ensure(wbytes + 256 + extra_bytes)) return -2;
     std::vector<WArgs> hw(batch);
     for (int p = 0; p < batch; ++p) { hw[p].x = h_x[p]; hw[p].xc = fp_pow_u64(h_x[p], CHUNK); hw[p].xt = fp_pow_u64(h_x[p], TILE); }
-    *d_w = ws.scratch.as<WArgs>();
-    B200_CUDA(cudaMemcpyAsync(*d_w, hw.data(), wbytes, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaStreamSynchronize(st));   // hw is a stack temporary
+    if (ws.scratch.ensure(wbytes + 256 + extra_bytes)) return -2;
     *d_extra = ws.scratch.as<uint8_t>() + ((wbytes + 255) & ~(size_t)255);
+    *d_w = reinterpret_cast<WArgs*>(ws.ring.push(hw.data(), wbytes, st));
+    if (!*d_w) {
+        *d_w = ws.scratch.as<WArgs>();
+        B200_CUDA(cudaMemcpyAsync(*d_w, hw.data(), wbytes, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaStreamSynchronize(st));   // hw is a stack temporary
+    }
     return 0;
 }
 

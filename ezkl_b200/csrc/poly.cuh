@@ -7,7 +7,7 @@ namespace b200 {
 
 enum PolyOp { POLY_ADD = 0, POLY_SUB = 1, POLY_MUL = 2, POLY_SCALE = 3, POLY_AXPY = 4 };
 
-struct PolyWorkspace { DevBuf scratch; };
+struct PolyWorkspace { DevBuf scratch; StagingRing ring; };
 
 // out[i] = a[i] (+|-|*) b[i]  |  a[i]*s  |  a[i] + s*b[i]        (all device pointers; out may alias a or b)
 int poly_binary(int op, const Fr* a, const Fr* b, const Fr* h_s, Fr* out, size_t n, cudaStream_t st);   // h_s: host scalar

@@ -78,10 +78,13 @@ int quotient_eval_run(const Fr* const* h_col_ptrs, size_t n_cols, uint32_t ext_k
     if (n_loads) memcpy(blob.data() + o_loads, h_loads, sizeof(QLoad) * n_loads);
     if (n_consts) memcpy(blob.data() + o_consts, h_consts, sizeof(Fr) * n_consts);
     if (n_instr) memcpy(blob.data() + o_prog, h_prog, sizeof(QInstr) * n_instr);
-    if (ws.prog.ensure(total)) return -2;
-    B200_CUDA(cudaMemcpyAsync(ws.prog.p, blob.data(), total, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaStreamSynchronize(st));      // blob is a stack temporary
-    uint8_t* d = ws.prog.as<uint8_t>();
+    uint8_t* d = reinterpret_cast<uint8_t*>(ws.ring.push(blob.data(), total, st));
+    if (!d) {
+        if (ws.prog.ensure(total)) return -2;
+        B200_CUDA(cudaMemcpyAsync(ws.prog.p, blob.data(), total, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaStreamSynchronize(st));      // blob is a stack temporary
+        d = ws.prog.as<uint8_t>();
+    }
     k_quotient_eval<<<div_up(N, 128), 128, 0, st>>>(reinterpret_cast<const Fr* const*>(d + o_cols), N - 1, reinterpret_cast<const QLoad*>(d + o_loads),
                                                      reinterpret_cast<const Fr*>(d + o_consts), reinterpret_cast<const QInstr*>(d + o_prog), (uint32_t)n_instr, d_out);
     B200_CUDA(cudaGetLastError());

@@ -13,7 +13,7 @@ static constexpr int Q_MAX_SLOTS = 32;
 struct QInstr { uint32_t op_dst; uint32_t a, b; };      // op_dst = op | (dst_slot << 8)
 struct QLoad { uint32_t column; uint32_t offset; };      // element offset already reduced mod 2^ext_k
 
-struct QuotientWorkspace { DevBuf prog; };
+struct QuotientWorkspace { DevBuf prog; StagingRing ring; };
 
 // out[idx] = program(columns[c][(idx + offset) mod N], constants) for idx < N = 2^ext_k.  h_* are host arrays.
 int quotient_eval_run(const Fr* const* h_col_ptrs /*device addresses*/, size_t n_cols, uint32_t ext_k, const QLoad* h_loads, size_t n_loads,
