@@ -47,7 +47,6 @@ def trace_ops(tr):
     """Expands a trace into op groups: (kind, count) in create_proof order."""
     A, L, Z, I, Q = tr["advice"], tr["lookups"], tr["perm_z"], tr["instance"], tr["quotient_pieces"]
     ncoset = A + I + Z + 2 * L                      # columns that go coeff -> extended coset for the quotient
-    npolys = A + tr["fixed"] + tr["perm_cols"] + Z + 2 * L + 1 + Q
     return [
         ("msm_lagrange", A),                        # stage 1: advice commitments
         ("msm_lagrange", L),                        # stage 2: lookup multiplicities m(X)
@@ -180,7 +179,6 @@ def run_b200(args):
     programs = {}
     d_ext = 1 << tr["ext_bits"]
     tinv_local = np.ascontiguousarray(np.stack([dom.t_evaluations[(rank + world * t) % d_ext] for t in range(max(1, d_ext // world))]))
-    host_h = torch.empty((tr["quotient_pieces"] * n, 4), dtype=torch.int64).pin_memory()
 
     def quotient_stage(get_col, put_h):
         """Stages 6-7.  Coset NTTs are dealt by column; evaluate_h runs row-cyclic (row idx on rank idx mod world): since

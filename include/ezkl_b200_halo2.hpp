@@ -127,6 +127,33 @@ inline std::vector<Fr> kate_division(const std::vector<Fr>& a, const Fr& b) {
     return q;
 }
 
+// multiopen / SHPLONK linear combination q(X) = sum_j scalars[j] * polys[j](X) in one pass
+inline std::vector<Fr> poly_lincomb(const std::vector<const Fr*>& polys, const std::vector<Fr>& scalars, size_t n) {
+    if (polys.size() != scalars.size()) throw std::runtime_error("poly_lincomb: polys / scalars length mismatch");
+    std::vector<Fr> out(n);
+    check(b200_poly_lincomb(polys.data(), scalars.data(), polys.size(), n, out.data()), "poly_lincomb");
+    return out;
+}
+
+// ---- plonk/evaluation.rs ---------------------------------------------------------------------------------------------
+// A lowered GraphEvaluator program (see include/ezkl_b200.h for the operand encoding); evaluate_h runs it once per row of the
+// extended domain.  columns[c] has 2^extended_k elements; rotations are in rows of the original domain.
+struct QuotientProgram {
+    std::vector<b200_col_ref> loads;
+    std::vector<Fr> constants;
+    std::vector<b200_instr> instructions;
+    static uint32_t slot(uint32_t i) { return i; }
+    static uint32_t constant(uint32_t i) { return (1u << 30) | i; }
+    static uint32_t load(uint32_t i) { return (2u << 30) | i; }
+    void push(uint32_t op, uint32_t dst_slot, uint32_t a, uint32_t b = 0) { instructions.push_back(b200_instr{op | (dst_slot << 8), a, b}); }
+};
+inline std::vector<Fr> evaluate_h(const QuotientProgram& prog, const std::vector<const Fr*>& columns, uint32_t k, uint32_t extended_k) {
+    std::vector<Fr> out((size_t)1 << extended_k);
+    check(b200_quotient_eval(columns.data(), columns.size(), k, extended_k, prog.loads.data(), prog.loads.size(), prog.constants.data(),
+                             prog.constants.size(), prog.instructions.data(), prog.instructions.size(), out.data()), "evaluate_h");
+    return out;
+}
+
 // ---- poly/domain.rs -------------------------------------------------------------------------------------------------
 class EvaluationDomain {
 public:

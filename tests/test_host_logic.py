@@ -134,3 +134,19 @@ def test_proving_key_reader_on_reference_fixture():
     assert np.array_equal(pk.permutation_cosets[0], g["perm_cosets_0"]) and np.array_equal(pk.l_active_row, g["l_active_row"])
     with pytest.raises(nat.B200Error):
         h2.ProvingKey.read(path, num_permutation_columns=31, num_selectors=80)      # wrong layout is detected, not mis-parsed
+
+
+def test_bench_reference_arm_prints_contract_json():
+    """`bench.py --impl reference` (the CPU port arm the driver runs first) prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--k", "8", "--steps", "1", "--warmup", "0", "--cpu-budget", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["higher_is_better"] is False and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
