@@ -299,6 +299,14 @@ int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void
     if (!rc) g_launches += 1;
     return rc;
 }
+int b200_g1_fixed_base_mul_dev(const void* d_scalars, size_t n, const b200_g1_affine* base, void* d_out_affine, void* stream) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(d_scalars && base && d_out_affine, -1, "g1_fixed_base_mul: null pointer");
+    G1Affine b; memcpy(&b, base, sizeof b);
+    int rc = g1_fixed_base_mul_run(reinterpret_cast<const Fr*>(d_scalars), n, b, reinterpret_cast<G1Affine*>(d_out_affine), pick_stream(c, stream));
+    if (!rc && n) g_launches += 1;
+    return rc;
+}
 int b200_g1_generate_dev(uint64_t seed, size_t n, void* d_out_affine, void* stream) {
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(d_out_affine, -1, "g1_generate: null pointer");

@@ -339,6 +339,26 @@ int g1_generate_run(uint64_t seed, size_t n, G1Affine* d_out, cudaStream_t st) {
     return 0;
 }
 
+// out[i] = [scalars[i]] * base (affine): the n fixed-base multiplications of ParamsKZG::new / gen_srs
+__global__ void __launch_bounds__(128) k_g1_fixed_base_mul(const Fr* __restrict__ scalars, size_t n, G1Affine base, G1Affine* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr s = fp_from_mont(fp_load(scalars + i));
+    G1Xyzz acc = g1_xyzz_identity();
+#pragma unroll 1
+    for (int b = 253; b >= 0; --b) {
+        acc = g1_dbl(acc);
+        if ((s.l[b >> 5] >> (b & 31)) & 1) acc = g1_add_mixed(acc, base);
+    }
+    out[i] = g1_to_affine(acc);
+}
+int g1_fixed_base_mul_run(const Fr* d_scalars, size_t n, const G1Affine& base, G1Affine* d_out, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_g1_fixed_base_mul<<<div_up(n, 128), 128, 0, st>>>(d_scalars, n, base, d_out);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int g1_sum_run(const G1Xyzz* d_points, size_t groups, size_t count, G1Xyzz* d_out, cudaStream_t st) {
     if (groups == 0) return 0;
     B200_CHECK(groups <= 0x7fffffffu && count <= 0xffffffffu, -1, "g1_sum: sizes out of range");

@@ -27,6 +27,7 @@ void msm_table_free(MsmTable* t);
 // out[b] = sum_i scalars[b*stride + i] * P_i   (i < n <= table.n), XYZZ form, one point per column, on device.
 int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int batch, G1Xyzz* d_out,
             MsmWorkspace& ws, cudaStream_t st);
+int g1_fixed_base_mul_run(const Fr* d_scalars, size_t n, const G1Affine& base, G1Affine* d_out, cudaStream_t st);
 int g1_generate_run(uint64_t seed, size_t n, G1Affine* d_out, cudaStream_t st);
 // out[g] = sum_j points[g*count + j]
 int g1_sum_run(const G1Xyzz* d_points, size_t groups, size_t count, G1Xyzz* d_out, cudaStream_t st);

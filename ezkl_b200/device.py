@@ -38,6 +38,40 @@ def generate_bases(n: int, seed: int = 0xE2C1B200) -> torch.Tensor:
     return out
 
 
+def fixed_base_mul(scalars: torch.Tensor, base=None) -> torch.Tensor:
+    """scalars [n,4] (Montgomery wire) -> [n,8] affine points [scalar_i] * base (default: the G1 generator (1, 2))."""
+    _chk(scalars, 4)
+    n = scalars.numel() // 4
+    if base is None:
+        base = np.concatenate([F.fq_to_limbs(1), F.fq_to_limbs(2)])
+    base = nat.as_u64(base, 8)
+    out = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    nat.check(nat.lib().b200_g1_fixed_base_mul_dev(nat.dev(scalars.data_ptr()), C.c_size_t(n), nat.ptr(base), nat.dev(out.data_ptr()), _stream()))
+    return out
+
+
+def constant_column(value_int: int, n: int) -> torch.Tensor:
+    t = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    t[:] = torch.from_numpy(F.fr_to_limbs(value_int).view(np.int64)).cuda()
+    return t
+
+
+def setup_srs(k: int, s: int):
+    """ParamsKZG::new / setup with a caller-chosen trapdoor s (gen_srs, /root/reference/src/pfsys/srs.rs:14-16), all on the device:
+    g[i] = [s^i] G,  g_lagrange[i] = [L_i(s)] G with L_i(s) = omega^i (s^n - 1) / (n (s - omega^i)).  Returns (g, g_lagrange) [n,8]."""
+    r = F.FR_MODULUS
+    n = 1 << k
+    omega = pow(F.FR_ROOT_OF_UNITY, 1 << (F.FR_S - k), r)
+    one = F.fr_to_limbs(1)
+    s_pows = prefix_scan(constant_column(s, n), one, True)                      # s^i
+    w_pows = prefix_scan(constant_column(omega, n), one, True)                  # omega^i
+    den = poly_op("sub", constant_column(s, n), w_pows)                         # s - omega^i  (s must not be an n-th root of unity)
+    batch_invert(den)
+    lag = poly_op("mul", w_pows, den)
+    poly_op("scale", lag, s=F.fr_to_limbs((pow(s, n, r) - 1) * F.fr_inv(n) % r), out=lag)
+    return fixed_base_mul(s_pows), fixed_base_mul(lag)
+
+
 def random_scalars(n: int, batch: int | None = None, seed: int = 0, small_bits: int | None = None) -> torch.Tensor:
     """Uniform scalars < 2^252 (or < 2^small_bits) in Montgomery wire form, generated on the device with torch's RNG."""
     g = torch.Generator(device="cuda")

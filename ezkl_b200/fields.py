@@ -27,3 +27,8 @@ def fr_from_limbs(a) -> int:
 
 def fr_inv(x: int) -> int:
     return pow(x, -1, FR_MODULUS)
+
+
+def fq_to_limbs(x: int) -> np.ndarray:
+    m = (x % FQ_MODULUS) * _R % FQ_MODULUS
+    return np.array([(m >> (64 * i)) & _MASK for i in range(4)], dtype=np.uint64)

@@ -288,6 +288,14 @@ class ParamsKZG:
         gl = np.frombuffer(d, dtype="<u8", count=8 * n, offset=4 + 64 * n).reshape(n, 8).copy()
         return cls(k, g, gl, d[4 + 128 * n:])
 
+    @classmethod
+    def setup(cls, k: int, s: int) -> "ParamsKZG":
+        """ParamsKZG::new(k) with a caller-supplied trapdoor (the reference's gen_srs uses OsRng; test / bench SRS only).
+        The G2 half is not produced: it never reaches the prover's MSMs."""
+        from . import device as dev
+        g, gl = dev.setup_srs(k, s)
+        return cls(k, dev.to_host(g), dev.to_host(gl), b"")
+
     def write(self, path: str):
         with open(path, "wb") as f:
             f.write(struct.pack("<I", self.k) + self.g.tobytes() + self.g_lagrange.tobytes() + self._tail)

@@ -67,6 +67,9 @@ int b200_msm_batch(uint64_t bases, const b200_fr* const* scalars, size_t n, size
 int b200_msm_batch_dev(uint64_t bases, const void* d_scalars, size_t n, size_t stride, size_t batch, void* d_out_xyzz, void* stream);
 /* out[g] = sum_{j < count} points[g*count + j] (device XYZZ arrays): the local add after an all-gather of per-rank partials */
 int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void* d_out_xyzz, void* stream);
+/* out[i] = [scalars[i]] * base, affine: the n fixed-base multiplications behind ParamsKZG::new / gen_srs
+ * (/root/reference/src/pfsys/srs.rs:14-16: g[i] = [s^i] G, g_lagrange[i] = [L_i(s)] G).  Device pointers. */
+int b200_g1_fixed_base_mul_dev(const void* d_scalars, size_t n, const b200_g1_affine* base, void* d_out_affine, void* stream);
 /* synthetic SRS-shaped bases for benchmarks: out[i] = [splitmix(seed, i)] * G, affine, pairwise distinct w.h.p. */
 int b200_g1_generate_dev(uint64_t seed, size_t n, void* d_out_affine, void* stream);
 /* host: XYZZ partials -> normalised Jacobian (one shared inversion) */

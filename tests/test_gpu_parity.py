@@ -476,3 +476,30 @@ def test_kzg_open_identity_with_known_trapdoor():
     rhs = orc.g1_scalar_mul(cq, H.fr_array([(s - x) % pyref.R]))
     assert np.array_equal(lhs, rhs)
     bases.release()
+
+
+def test_gen_srs_and_commit_consistency():
+    """gen_srs (src/pfsys/srs.rs:14-16) on the device with a known trapdoor s: g[i] = [s^i]G and g_lagrange[i] = [L_i(s)]G against
+    the oracle's scalar multiplication, the fixture relation g_lagrange = n^-1 sum w^-ij g[i], and the identity that ties MSM
+    and NTT together: commit_lagrange(values) == commit(lagrange_to_coeff(values)) == [p(s)]G."""
+    rng = random.Random(31)
+    k = 7
+    n = 1 << k
+    s = rng.randrange(2, pyref.R)
+    params = h2.ParamsKZG.setup(k, s)
+    G = np.array(list(H.fq_wire(1)) + list(H.fq_wire(2)), np.uint64)
+    pw, cur = [], 1
+    for _ in range(n):
+        pw.append(cur)
+        cur = cur * s % pyref.R
+    assert np.array_equal(params.g, orc.g1_scalar_mul(np.tile(G, (n, 1)), H.fr_array(pw)))
+    w = pyref.omega_for(k)
+    lag = [pow(w, i, pyref.R) * (pow(s, n, pyref.R) - 1) * pow(n * (s - pow(w, i, pyref.R)), -1, pyref.R) % pyref.R for i in range(n)]
+    assert np.array_equal(params.g_lagrange, orc.g1_scalar_mul(np.tile(G, (n, 1)), H.fr_array(lag)))
+    vals = orc.gen_scalars(n, seed=9)
+    dom = h2.EvaluationDomain(2, k)
+    coeffs = dom.lagrange_to_coeff(vals)
+    c1 = jac_to_affine(params.commit_lagrange(vals))[0]
+    c2 = jac_to_affine(params.commit(coeffs))[0]
+    ps = H.fr_unwire(h2.eval_polynomial(coeffs, H.fr_wire(s)))
+    assert np.array_equal(c1, c2) and np.array_equal(c1, orc.g1_scalar_mul(G.reshape(1, 8), H.fr_array([ps]))[0])
