@@ -289,11 +289,16 @@ __global__ void __launch_bounds__(TREE_THREADS) k_reduce(const G1Xyzz* __restric
     G1Xyzz run = g1_xyzz_identity(), acc = g1_xyzz_identity();
     if (lo < nbuckets) {
         const uint32_t hi = min(lo + per_thread, nbuckets);
+        // software-pipelined running sums: acc += run_i and run_{i+1} = run_i + B are independent, so the two group
+        // additions of one iteration overlap (the tail of a small batch is latency-bound, not issue-bound)
+        run = bs[hi - 1];
 #pragma unroll 1
-        for (uint32_t b = hi; b-- > lo;) {
-            run = g1_add(run, bs[b]);
-            acc = g1_add(acc, run);
+        for (uint32_t b = hi - 1; b-- > lo;) {
+            const G1Xyzz prev = run;
+            run = g1_add(prev, bs[b]);
+            acc = g1_add(acc, prev);
         }
+        acc = g1_add(acc, run);
         if (lo > 0) acc = g1_add(acc, g1_mul_small(run, lo));
     }
     acc = block_sum(acc, sh);
