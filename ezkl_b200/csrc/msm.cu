@@ -71,8 +71,10 @@ void msm_table_free(MsmTable* t) {
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, size_t stride, uint32_t n, uint32_t table_n, int c, int W,
                                                  uint32_t nbuckets, uint32_t* __restrict__ counters /*[col][nbuckets]*/,
-                                                 const uint32_t* __restrict__ offs /*[col][nbuckets+1]*/, uint32_t* __restrict__ ents, size_t ent_stride) {
+                                                 const uint32_t* __restrict__ offs /*[col][nbuckets+1]*/, uint32_t* __restrict__ ents, size_t ent_stride,
+                                                 const uint32_t* __restrict__ skew) {
     const uint32_t col = blockIdx.y;
+    const bool aggregate = !SCATTER || skew[col] != 0;        // the counting pass cannot know yet; the scatter pass can
     const Fr* sc = scalars + (size_t)col * stride;
     uint32_t* cnt = counters + (size_t)col * nbuckets;
     const uint32_t* off = SCATTER ? offs + (size_t)col * (nbuckets + 1) : nullptr;
@@ -89,7 +91,10 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
             int32_t d = msm_next_digit(s.l, c, &carry);
             const bool nz = d != 0;     // invalid lanes carry s = 0 -> all digits 0
             const unsigned act = __ballot_sync(0xffffffffu, nz);
-            if (nz) {
+            if (nz && !aggregate) {
+                const uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1u;
+                ent[off[bucket] + atomicAdd(&cnt[bucket], 1u)] = ((uint32_t)w * table_n + i) | (d < 0 ? 0x80000000u : 0u);
+            } else if (nz) {
                 const uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1u;
                 const unsigned peers = __match_any_sync(act, bucket);
                 const int leader = __ffs(peers) - 1;
@@ -107,7 +112,10 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
 
 // 2: one block per column. offs = exclusive scan of counts; chunk_offs = exclusive scan of ceil(count / cap).
 __global__ void __launch_bounds__(1024) k_scan_buckets(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offs, uint32_t* __restrict__ chunk_offs,
-                                                        uint32_t nbuckets, uint32_t cap) {
+                                                        uint32_t nbuckets, uint32_t cap, uint32_t* __restrict__ skew /*[col]*/) {
+    __shared__ uint32_t sh_max;
+    if (threadIdx.x == 0) sh_max = 0;
+    __syncthreads();
     const uint32_t col = blockIdx.x;
     const uint32_t* cnt = counts + (size_t)col * nbuckets;
     uint32_t* off = offs + (size_t)col * (nbuckets + 1);
@@ -115,12 +123,19 @@ __global__ void __launch_bounds__(1024) k_scan_buckets(const uint32_t* __restric
     const uint32_t ipt = (nbuckets + blockDim.x - 1) / blockDim.x;
     const uint32_t lo = threadIdx.x * ipt, hi = min(lo + ipt, nbuckets);
     uint32_t s = 0, cs = 0;
-    for (uint32_t b = lo; b < hi; ++b) { uint32_t v = cnt[b]; s += v; cs += (v + cap - 1) / cap; }
+    uint32_t mx = 0;
+    for (uint32_t b = lo; b < hi; ++b) { uint32_t v = cnt[b]; s += v; cs += (v + cap - 1) / cap; mx = max(mx, v); }
+    if (mx) atomicMax(&sh_max, mx);
     uint32_t tot, ctot;
     uint32_t ex = block_exclusive_scan(s, &tot);
     uint32_t cex = block_exclusive_scan(cs, &ctot);
     for (uint32_t b = lo; b < hi; ++b) { uint32_t v = cnt[b]; off[b] = ex; coff[b] = cex; ex += v; cex += (v + cap - 1) / cap; }
-    if (threadIdx.x == 0) { off[nbuckets] = tot; coff[nbuckets] = ctot; }
+    if (threadIdx.x == 0) {
+        off[nbuckets] = tot; coff[nbuckets] = ctot;
+        // a column is "skewed" when some bucket holds far more than its share: only then is warp-level aggregation of the
+        // scatter atomics worth its MATCH / SHFL cost (uniform scalars almost never collide inside a warp)
+        skew[col] = sh_max > 16u * (tot / nbuckets + 1u) ? 1u : 0u;
+    }
 }
 
 // 4: chunk table (start, len) + histogram of lengths + list of heavy buckets
@@ -415,10 +430,11 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     uint32_t* heavy = len_cursor + n_len;
     // offsets: offs | chunk_offs | len_offs
     const size_t n_off = (size_t)batch * (nb + 1);
-    if (ws.offs.ensure((2 * n_off + n_len) * 4)) return -2;
+    if (ws.offs.ensure((2 * n_off + n_len + (size_t)batch) * 4)) return -2;
     uint32_t* offs = ws.offs.as<uint32_t>();
     uint32_t* chunk_offs = offs + n_off;
     uint32_t* len_offs = chunk_offs + n_off;
+    uint32_t* skew = len_offs + n_len;
     if (ws.ents.ensure((size_t)batch * ent_stride * 4)) return -2;
     uint32_t* ents = ws.ents.as<uint32_t>();
     if (ws.subs.ensure((size_t)batch * chunk_stride * 4 * 3)) return -2;
@@ -435,9 +451,9 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     B200_CUDA(cudaMemsetAsync(hist, 0, counts_words * 4, st));
     const unsigned dig_blocks = min(div_up(n, 256), 148u * 8u);
     dim3 gd(dig_blocks, batch);
-    k_digits<false><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, c, W, nb, hist, nullptr, nullptr, 0);
-    k_scan_buckets<<<batch, 1024, 0, st>>>(hist, offs, chunk_offs, nb, cap);
-    k_digits<true><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, c, W, nb, cursor, offs, ents, ent_stride);
+    k_digits<false><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, c, W, nb, hist, nullptr, nullptr, 0, nullptr);
+    k_scan_buckets<<<batch, 1024, 0, st>>>(hist, offs, chunk_offs, nb, cap, skew);
+    k_digits<true><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, c, W, nb, cursor, offs, ents, ent_stride, skew);
     k_fill_chunks<<<dim3(div_up(nb, 256), batch), 256, (cap + 1) * 4, st>>>(offs, chunk_offs, nb, cap, chunk_start, chunk_len, chunk_stride, len_hist, heavy, heavy_stride);
     k_len_offsets<<<batch, 32, 0, st>>>(len_hist, len_offs, cap);
     const unsigned ch_blocks = min(div_up(chunk_stride, 256), 148u * 8u);
