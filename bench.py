@@ -376,6 +376,9 @@ def run_b200(args):
             my_msm_cols += len(mine(count, gidx))
         gidx += count
     acc_ms, acc_cnt = prof["msm_accumulate"]
+    _c, _w = C.c_int(0), C.c_int(0)
+    nat.check(L.b200_bases_info(C.c_uint64(g_lag.handle), None, C.byref(_c), C.byref(_w)))
+    win = _w.value                                  # windows per scalar = bucket additions per (scalar, base) pair
     launch_cols = my_msm_cols * args.steps / max(acc_cnt, 1)
     alg_bytes_per_launch = launch_cols * n * (32.0 + 64.0 / max(launch_cols, 1.0))
     achieved = alg_bytes_per_launch / ((acc_ms / max(acc_cnt, 1)) * 1e-3) / 1e9 if acc_ms > 0 else 0.0
@@ -404,6 +407,11 @@ def run_b200(args):
         "roofline": {"kernel": "k_accumulate (MSM bucket accumulation)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes_per_launch), "avg_launch_ms": round(acc_ms / max(acc_cnt, 1), 4),
+                     "kernel_share_of_step": round(acc_ms / args.steps / ms_dev, 4) if ms_dev > 0 else None,
+                     "issue_bound": {"what": "bucket additions (XYZZ += affine, 8M+2S = 10.4 multiply-equivalents) per second against the measured "
+                                             "254-bit multiply ceiling of 67.5 G mulmod/s (profiles/r01_microbench_mulmod.txt)",
+                                     "adds_per_s": round(my_msm_cols * n * win / (acc_ms / args.steps * 1e-3), 1) if acc_ms > 0 else None,
+                                     "frac": round(my_msm_cols * n * win * 10.4 / (acc_ms / args.steps * 1e-3) / 67.5e9, 4) if acc_ms > 0 else None},
                      "note": "integer-issue bound (254-bit modular arithmetic), not HBM bound: see DESIGN.md"},
         "msm_pairs_per_s": round(pairs / world / (msm_ms * 1e-3), 1) * world if msm_ms > 0 else None,
         "ntt_elts_per_s": round(ntt_elts / world / (ntt_ms * 1e-3), 1) * world if ntt_ms > 0 else None,
