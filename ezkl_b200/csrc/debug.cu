@@ -2,6 +2,7 @@
 // (field arithmetic, group law, digit recoding) before the composite kernels are blamed.  Not part of the drop-in ABI.
 #include "../../include/ezkl_b200.h"
 #include "msm.cuh"
+#include "fp30.cuh"
 
 namespace b200 {
 template <class Tag>
@@ -145,6 +146,27 @@ int b200_debug_digits(const b200_fr* s, size_t n, int c, int32_t* out /* n * cei
     cudaFree(ds); cudaFree(dout);
     return 0;
 }
+// variant 5 of the throughput microbenchmark: chain of carry-less 9 x 30-bit multiplications (fp30.cuh)
+__global__ void __launch_bounds__(256) k_bench_mul30(uint32_t* out, int iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    b200::Fq30 x, y;
+    for (int i = 0; i < 9; ++i) { x.l[i] = (t * 2654435761u + i * 40503u) & 0x3fffffffu; y.l[i] = (t ^ (i * 0x9e3779b9u)) & 0x3fffffffu; }
+    x.l[8] &= 0x3fff; y.l[8] &= 0x3fff;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) { b200::Fq30 r; b200::fq30_mul(r, x, y); x = r; }
+    uint32_t acc = 0;
+    for (int i = 0; i < 9; ++i) acc ^= x.l[i];
+    out[t] = acc;
+}
+int b200_debug_host_fq30_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        b200::Fq30 x, y, r;
+        memcpy(x.l, a + 9 * i, 36); memcpy(y.l, b + 9 * i, 36);
+        b200::fq30_mul(r, x, y);
+        memcpy(out + 9 * i, r.l, 36);
+    }
+    return 0;
+}
 // returns elapsed ms for `iters` operations per thread on blocks x threads threads
 int b200_debug_bench(int variant, int iters, int blocks, int threads, float* ms) {
     Fq* d; B200_CUDA(cudaMalloc(&d, sizeof(Fq) * (size_t)blocks * threads));
@@ -156,6 +178,7 @@ int b200_debug_bench(int variant, int iters, int blocks, int threads, float* ms)
             case 1: k_bench_mul<1><<<blocks, threads>>>(d, iters); break;
             case 2: k_bench_mul<2><<<blocks, threads>>>(d, iters); break;
             case 3: k_bench_mul<3><<<blocks, threads>>>(d, iters); break;
+            case 5: k_bench_mul30<<<blocks, threads>>>(reinterpret_cast<uint32_t*>(d), iters); break;
             default: k_bench_mul<4><<<blocks, threads>>>(d, iters); break;
         }
         cudaEventRecord(e1);

@@ -150,3 +150,21 @@ def test_bench_reference_arm_prints_contract_json():
         assert key in line, key
     assert line["impl"] == "reference" and line["higher_is_better"] is False and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_experimental_carryless_30bit_multiply_vs_bigint():
+    """fp30.cuh (round-2 candidate): 9 x 30-bit-limb Montgomery multiply with 64-bit column accumulators, host build."""
+    L = nat.lib()
+    P, R30 = pyref.P, 1 << 270
+    rng = random.Random(3)
+    xs = [rng.randrange(P) for _ in range(400)] + [0, 1, P - 1, 2 * P - 1]
+    ys = [rng.randrange(P) for _ in range(400)] + [P - 1, P - 1, P - 1, 2 * P - 1]
+    lim = lambda v: [(v >> (30 * i)) & 0x3FFFFFFF for i in range(9)]
+    a = np.array([lim(x) for x in xs], dtype=np.uint32)
+    b = np.array([lim(y) for y in ys], dtype=np.uint32)
+    out = np.zeros_like(a)
+    assert L.b200_debug_host_fq30_mul(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(len(xs))) == 0
+    rinv = pow(R30, -1, P)
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        v = sum(int(out[i, j]) << (30 * j) for j in range(9))
+        assert v % P == x * y * rinv % P and v < 2 * P and all(int(out[i, j]) < (1 << 30) for j in range(8))

@@ -17,9 +17,9 @@ from ezkl_b200 import halo2 as h2  # noqa: E402
 
 def microbench():
     L = nat.lib()
-    names = {0: "fq mul chain (PTX)", 1: "fq mul 2 chains (PTX)", 2: "fq mul portable", 3: "xyzz mixed add", 4: "fq add+sub pair"}
-    for variant in (0, 1, 2, 3, 4):
-        for threads, blocks_per_sm in ((128, 4), (256, 2), (256, 4), (256, 8), (1024, 2)):
+    names = {0: "fq mul chain (PTX)", 1: "fq mul 2 chains (PTX)", 2: "fq mul portable", 3: "xyzz mixed add", 4: "fq add+sub pair", 5: "fq mul 9x30-bit carry-less"}
+    for variant in (0, 5, 1, 2, 3, 4):
+        for threads, blocks_per_sm in ((128, 4), (256, 2), (256, 4), (256, 8)):
             if variant == 3 and threads * blocks_per_sm > 512:
                 continue
             iters = 2000 if variant != 3 else 200
