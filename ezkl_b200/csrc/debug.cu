@@ -1,6 +1,7 @@
 // debug.cu — small self-test entry points (b200_debug_*) used only by tests/ to localise a failure to one layer
 // (field arithmetic, group law, digit recoding) before the composite kernels are blamed.  Not part of the drop-in ABI.
 #include "../../include/ezkl_b200.h"
+#include <vector>
 #include "msm.cuh"
 #include "fp30.cuh"
 
@@ -166,6 +167,18 @@ int b200_debug_host_fq30_mul(const uint32_t* a, const uint32_t* b, uint32_t* out
         memcpy(out + 9 * i, r.l, 36);
     }
     return 0;
+}
+// CPU run of the batched-affine accumulation bodies (msm_affine.cuh) on host arrays: out[c] = sum of the chunk's points
+int b200_debug_host_affine_chunks(const b200_g1_affine* table, const uint32_t* ents, size_t n_ents, const uint32_t* chunk_start,
+                                  const uint32_t* chunk_len, size_t nchunks, b200_g1_affine* out) {
+    std::vector<b200::G1Affine> tab, res(nchunks);
+    size_t n_pts = 0;
+    for (size_t i = 0; i < n_ents; ++i) if ((ents[i] & 0x7fffffffu) + 1 > n_pts) n_pts = (ents[i] & 0x7fffffffu) + 1;
+    tab.resize(n_pts);
+    memcpy(tab.data(), table, 64 * n_pts);
+    int rc = b200::msm_affine_host_chunks(tab.data(), ents, n_ents, chunk_start, chunk_len, nchunks, res.data());
+    memcpy(out, res.data(), 64 * nchunks);
+    return rc;
 }
 // returns elapsed ms for `iters` operations per thread on blocks x threads threads
 int b200_debug_bench(int variant, int iters, int blocks, int threads, float* ms) {

@@ -16,6 +16,7 @@
 //  11 k_final           per-column sum of the block partials -> one XYZZ point per column
 // HBM traffic per (scalar, base) pair: 32 B scalar (read twice) + W x 64 B table gathers; the kernel is bound by
 // integer issue (IMAD.WIDE), not HBM — see DESIGN.md §kernels.
+#include <cstdlib>
 #include "msm.cuh"
 
 namespace b200 {
@@ -413,7 +414,9 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const uint32_t nb = 1u << (c - 1);
     const size_t ent_stride = (size_t)n * W;
     B200_CHECK(ent_stride < ((size_t)1 << 32), -1, "msm: n*W too large");
-    const uint32_t cap = pick_cap(ent_stride * batch);
+    static const bool use_affine = getenv("B200_MSM_AFFINE") && atoi(getenv("B200_MSM_AFFINE")) != 0;
+    uint32_t cap = pick_cap(ent_stride * batch);
+    if (use_affine && cap > 128) cap = 128;          // the affine tree runs ceil(log2(cap)) rounds: keep it at 7
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
     const uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
@@ -459,7 +462,10 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const unsigned ch_blocks = min(div_up(chunk_stride, 256), 148u * 8u);
     k_order_chunks<<<dim3(ch_blocks, batch), 256, 0, st>>>(chunk_len, chunk_stride, chunk_offs, nb, len_offs, len_cursor, cap, order);
     const unsigned acc_blocks = min(div_up(chunk_stride, 128), 148u * 16u);
-    {
+    if (use_affine) {
+        ProfScope ps(PROF_MSM_ACCUMULATE, st);
+        if (int rc = msm_accumulate_affine(t, ents, ent_stride, chunk_start, chunk_len, order, chunk_stride, chunk_offs, nb, cap, batch, chunk_sums, ws.affine, st)) return rc;
+    } else {
         ProfScope ps(PROF_MSM_ACCUMULATE, st);
         k_accumulate<<<dim3(acc_blocks, batch), 128, 0, st>>>(t.d_table, ents, ent_stride, chunk_start, chunk_len, order, chunk_stride, chunk_offs, nb, chunk_sums);
     }

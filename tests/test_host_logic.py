@@ -168,3 +168,39 @@ def test_experimental_carryless_30bit_multiply_vs_bigint():
     for i, (x, y) in enumerate(zip(xs, ys)):
         v = sum(int(out[i, j]) << (30 * j) for j in range(9))
         assert v % P == x * y * rinv % P and v < 2 * P and all(int(out[i, j]) < (1 << 30) for j in range(8))
+
+
+def test_batched_affine_accumulation_bodies_on_host():
+    """msm_affine.cuh run on the CPU: every chunk's tree of batched-affine additions (hierarchical Montgomery trick) must equal
+    the plain sum of its points — incl. repeated points (doubling), P + (-P), identity entries, negated entries, length-1 chunks."""
+    L = nat.lib()
+    rng = random.Random(8)
+    npts = 300
+    table = orc.gen_bases(npts, seed=77, threads=2)
+    table[5] = 0                                            # an identity table entry
+    ents, starts, lens = [], [], []
+    shapes = [1, 2, 3, 4, 5, 7, 8, 16, 31, 33, 64, 100, 1, 2] + [rng.randrange(1, 40) for _ in range(80)]
+    for ln in shapes:
+        starts.append(len(ents))
+        lens.append(ln)
+        for _ in range(ln):
+            ents.append(rng.randrange(npts) | (0x80000000 if rng.random() < 0.3 else 0))
+    # crafted chunks: P + P, P + (-P), identity + P, P + P + P + P
+    for special in ([7, 7], [9, 9 | 0x80000000], [5, 11], [13, 13, 13, 13], [5, 5], [20, 20 | 0x80000000, 21]):
+        starts.append(len(ents))
+        lens.append(len(special))
+        ents.extend(special)
+    ents = np.array(ents, dtype=np.uint32)
+    starts = np.array(starts, dtype=np.uint32)
+    lens = np.array(lens, dtype=np.uint32)
+    out = np.zeros((len(lens), 8), np.uint64)
+    assert L.b200_debug_host_affine_chunks(nat.ptr(table), ents.ctypes.data_as(C.c_void_p), C.c_size_t(len(ents)), starts.ctypes.data_as(C.c_void_p),
+                                           lens.ctypes.data_as(C.c_void_p), C.c_size_t(len(lens)), nat.ptr(out)) == 0
+    for c in range(len(lens)):
+        acc = None
+        for e in ents[starts[c]:starts[c] + lens[c]]:
+            p = H.g1_unwire(table[int(e) & 0x7FFFFFFF])
+            if int(e) >> 31:
+                p = pyref.g1_neg(p)
+            acc = pyref.g1_add(acc, p)
+        assert H.g1_unwire(out[c]) == acc, (c, int(lens[c]))
