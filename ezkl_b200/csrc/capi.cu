@@ -299,6 +299,27 @@ int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void
     if (!rc) g_launches += 1;
     return rc;
 }
+int b200_g1_fft_dev(const void* d_in_affine, uint32_t log_n, const b200_fr* omega, const b200_fr* scale, void* d_out_affine, void* stream) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(d_in_affine && omega && d_out_affine, -1, "g1_fft: null pointer");
+    const Fr w = as_fr(omega);
+    Fr sc = fp_one<FrTag>();
+    if (scale) sc = as_fr(scale);
+    int rc = g1_fft_run(reinterpret_cast<const G1Affine*>(d_in_affine), log_n, w, scale ? &sc : nullptr, reinterpret_cast<G1Affine*>(d_out_affine), c->msm_ws.misc, pick_stream(c, stream));
+    if (!rc) g_launches += (uint64_t)g1_fft_launches(log_n);
+    return rc;
+}
+int b200_g1_fft(const b200_g1_affine* in, uint32_t log_n, const b200_fr* omega, const b200_fr* scale, b200_g1_affine* out) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(in && omega && out && log_n <= 26, -1, "g1_fft: bad argument");
+    const size_t n = (size_t)1 << log_n;
+    if (c->stage_a.ensure(sizeof(G1Affine) * n) || c->stage_b.ensure(sizeof(G1Affine) * n)) return -2;
+    B200_CUDA(cudaMemcpyAsync(c->stage_a.p, in, sizeof(G1Affine) * n, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = b200_g1_fft_dev(c->stage_a.p, log_n, omega, scale, c->stage_b.p, nullptr)) return rc;
+    B200_CUDA(cudaMemcpyAsync(out, c->stage_b.p, sizeof(G1Affine) * n, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
 int b200_g1_fixed_base_mul_dev(const void* d_scalars, size_t n, const b200_g1_affine* base, void* d_out_affine, void* stream) {
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CHECK(d_scalars && base && d_out_affine, -1, "g1_fixed_base_mul: null pointer");

@@ -35,6 +35,9 @@ void msm_table_free(MsmTable* t);
 int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int batch, G1Xyzz* d_out,
             MsmWorkspace& ws, cudaStream_t st);
 int g1_fixed_base_mul_run(const Fr* d_scalars, size_t n, const G1Affine& base, G1Affine* d_out, cudaStream_t st);
+// out[j] = scale * sum_i omega^(i j) * P_i over G1 (halo2 g_to_lagrange / ParamsKZG::downsize); affine in, affine out
+int g1_fft_run(const G1Affine* d_in, uint32_t log_n, const Fr& omega, const Fr* scale, G1Affine* d_out, DevBuf& scratch, cudaStream_t st);
+int g1_fft_launches(uint32_t log_n);
 int g1_generate_run(uint64_t seed, size_t n, G1Affine* d_out, cudaStream_t st);
 // out[g] = sum_j points[g*count + j]
 int g1_sum_run(const G1Xyzz* d_points, size_t groups, size_t count, G1Xyzz* d_out, cudaStream_t st);

@@ -263,6 +263,20 @@ class EvaluationDomain:
         return value * pow(self._omega, rotation % self.n, r) % r
 
 
+def g_to_lagrange(g, k: int) -> np.ndarray:
+    """halo2 poly/kzg/commitment.rs g_to_lagrange: best_fft over the group with omega^-1, then * n^-1, then normalise.
+    g: [2^k, 8] affine points -> the Lagrange-basis commitment key [2^k, 8]."""
+    g = nat.as_u64(g, 8)
+    n = 1 << k
+    assert g.shape[0] == n
+    r = F.FR_MODULUS
+    omega = pow(F.FR_ROOT_OF_UNITY, 1 << (F.FR_S - k), r)
+    out = np.zeros_like(g)
+    nat.ensure_init()
+    nat.check(nat.lib().b200_g1_fft(nat.ptr(g), C.c_uint32(k), nat.ptr(F.fr_to_limbs(F.fr_inv(omega))), nat.ptr(F.fr_to_limbs(F.fr_inv(n))), nat.ptr(out)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 # poly/kzg/commitment.rs
 class ParamsKZG:
@@ -295,6 +309,21 @@ class ParamsKZG:
         from . import device as dev
         g, gl = dev.setup_srs(k, s)
         return cls(k, dev.to_host(g), dev.to_host(gl), b"")
+
+    def downsize(self, new_k: int):
+        """ParamsKZG::downsize(k) as ezkl's load_params_prover uses it (/root/reference/src/execute.rs:1745-1748): keep the first
+        2^k monomial-basis points and rebuild the Lagrange-basis key with the group FFT."""
+        if new_k > self.k:
+            raise nat.B200Error("downsize: new k %d > current k %d" % (new_k, self.k))
+        if new_k == self.k:
+            return
+        n = 1 << new_k
+        for b in self._bases.values():
+            b.release()
+        self._bases = {}
+        self.k, self.n = new_k, n
+        self.g = np.ascontiguousarray(self.g[:n])
+        self.g_lagrange = g_to_lagrange(self.g, new_k)
 
     def write(self, path: str):
         with open(path, "wb") as f:

@@ -67,6 +67,11 @@ int b200_msm_batch(uint64_t bases, const b200_fr* const* scalars, size_t n, size
 int b200_msm_batch_dev(uint64_t bases, const void* d_scalars, size_t n, size_t stride, size_t batch, void* d_out_xyzz, void* stream);
 /* out[g] = sum_{j < count} points[g*count + j] (device XYZZ arrays): the local add after an all-gather of per-rank partials */
 int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void* d_out_xyzz, void* stream);
+/* FFT over G1: out[j] = scale * sum_i omega^(i*j) * in[i], 2^log_n affine points in and out (scale may be NULL = 1).
+ * halo2's g_to_lagrange = this with omega^-1 and scale = n^-1: the body of ParamsKZG::downsize, which ezkl runs whenever the SRS
+ * file is larger than the circuit (load_params_prover, /root/reference/src/execute.rs:1739-1750). */
+int b200_g1_fft(const b200_g1_affine* in, uint32_t log_n, const b200_fr* omega, const b200_fr* scale, b200_g1_affine* out);
+int b200_g1_fft_dev(const void* d_in_affine, uint32_t log_n, const b200_fr* omega, const b200_fr* scale, void* d_out_affine, void* stream);
 /* out[i] = [scalars[i]] * base, affine: the n fixed-base multiplications behind ParamsKZG::new / gen_srs
  * (/root/reference/src/pfsys/srs.rs:14-16: g[i] = [s^i] G, g_lagrange[i] = [L_i(s)] G).  Device pointers. */
 int b200_g1_fixed_base_mul_dev(const void* d_scalars, size_t n, const b200_g1_affine* base, void* d_out_affine, void* stream);

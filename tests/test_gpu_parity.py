@@ -503,3 +503,25 @@ def test_gen_srs_and_commit_consistency():
     c2 = jac_to_affine(params.commit(coeffs))[0]
     ps = H.fr_unwire(h2.eval_polynomial(coeffs, H.fr_wire(s)))
     assert np.array_equal(c1, c2) and np.array_equal(c1, orc.g1_scalar_mul(G.reshape(1, 8), H.fr_array([ps]))[0])
+
+
+def test_g_to_lagrange_reproduces_the_reference_srs_and_downsize():
+    """The reference's own SRS fixture is a known answer for the group FFT: g_lagrange == g_to_lagrange(g) (k = 6).  Then
+    ParamsKZG::downsize (src/execute.rs:1745-1748) to k = 4 against the defining relation computed with the oracle's MSM."""
+    k, g, gl = H.load_srs_fixture()
+    assert np.array_equal(h2.g_to_lagrange(g, k), gl)
+    params = h2.ParamsKZG.read(H.GOLDEN + "/kzg_k6.srs")
+    params.downsize(4)
+    n = 16
+    assert params.k == 4 and params.g.shape == (n, 8) and np.array_equal(params.g, g[:n])
+    w_inv = pow(pyref.omega_for(4), -1, pyref.R)
+    n_inv = pow(n, -1, pyref.R)
+    for j in range(n):
+        sc = H.fr_array([pow(w_inv, i * j, pyref.R) * n_inv % pyref.R for i in range(n)])
+        assert np.array_equal(params.g_lagrange[j], orc.msm(sc, g[:n], 2)), j
+    vals = orc.gen_scalars(n, seed=3)
+    dom = h2.EvaluationDomain(2, 4)
+    assert np.array_equal(params.commit_lagrange(vals), params.commit(dom.lagrange_to_coeff(vals)))
+    # a larger transform against the trapdoor SRS: g_to_lagrange([s^i]G) == [L_i(s)]G
+    p2 = h2.ParamsKZG.setup(9, 0x1234567)
+    assert np.array_equal(h2.g_to_lagrange(p2.g, 9), p2.g_lagrange)
