@@ -175,3 +175,45 @@ def test_permutation_product_and_lookup_sum():
         exp.append(acc)
         acc = (acc + sum(pow(c[i] + beta, -1, R) for c in ins) - mult[i] * pow(table[i] + beta, -1, R)) % R
     assert phi == exp and acc == 0
+
+
+@pytest.mark.gpu
+def test_shplonk_multiopen_flow_with_known_trapdoor():
+    """ProverSHPLONK mirror (ezkl_b200/multiopen.py) composed from the device primitives, on an SRS whose trapdoor s is known:
+    the quotient of every rotation set divides exactly, L(u) == 0, and both KZG relations hold in the exponent
+    (commit(h2) * (s - u) == commit(L); h(z) == sum_i v^i N_i(z) / Z_i(z) at a random z) — no pairing needed."""
+    from ezkl_b200 import _native as nat
+    from ezkl_b200 import halo2 as h2
+    from ezkl_b200 import multiopen as mo
+    nat.init(-1)
+    rng = random.Random(41)
+    k = 8
+    n = 1 << k
+    s = rng.randrange(2, R)
+    params = h2.ParamsKZG.setup(k, s)
+    w = pyref.omega_for(k)
+    x = rng.randrange(R)
+    polys = [orc.gen_scalars(n, seed=500 + i) for i in range(5)]
+    pts_a, pts_b, pts_c = [x, x * w % R], [x], [x, x * w % R, x * pow(w, -1, R) % R]
+    queries = []
+    for p, pts in ((polys[0], pts_a), (polys[1], pts_b), (polys[2], pts_a), (polys[3], pts_c), (polys[4], pts_b)):
+        queries += [mo.ProverQuery(pt, p) for pt in pts]
+    y, v, u = (rng.randrange(R) for _ in range(3))
+    prf = mo.create_proof(params, queries, y, v, u)
+    assert prf["must_be_zero"] == 0
+    assert len(prf["sets"]) == 3 and len(prf["super_points"]) == 3
+    z = rng.randrange(R)
+    zv = H.fr_wire(z)
+    ev = lambda poly: H.fr_unwire(h2.eval_polynomial(poly, zv))
+    vs = [pow(v, len(prf["sets"]) - 1 - i, R) for i in range(len(prf["sets"]))]
+    rhs = 0
+    for (points, _), num, vi in zip(prf["sets"], prf["numerators"], vs):
+        rhs = (rhs + vi * ev(num) * pow(mo.evaluate_vanishing_polynomial(points, z), -1, R)) % R
+    assert ev(prf["h_x"]) == rhs
+    assert ev(prf["h2_x"]) * (z - u) % R == ev(prf["l_x"])
+    # KZG in the exponent with the trapdoor
+    G = np.array(list(H.fq_wire(1)) + list(H.fq_wire(2)), np.uint64).reshape(1, 8)
+    sv = H.fr_wire(s)
+    assert np.array_equal(prf["h1"][:8], orc.g1_scalar_mul(G, H.fr_array([H.fr_unwire(h2.eval_polynomial(prf["h_x"], sv))]))[0])
+    lhs = orc.g1_scalar_mul(prf["h2"][:8].reshape(1, 8), H.fr_array([(s - u) % R]))
+    assert np.array_equal(lhs[0], params.commit(prf["l_x"])[:8])
