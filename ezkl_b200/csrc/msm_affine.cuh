@@ -83,16 +83,25 @@ HD bool aff_thread_chunk(const AffineArgs& a, uint64_t g, uint64_t* col, uint32_
     return true;
 }
 
-// Phase A: denominators of the thread's pairs; prefix product of pair j parked in pb_out[start + j].x
+// x coordinate (and only it) of an input point: half the bytes of the point, which is all phase A needs in the general case
+HD Fq aff_input_x(const AffineArgs& a, uint64_t col, uint32_t start, uint32_t idx) {
+    if (a.round == 0) return a.table[a.ents[col * a.ent_stride + start + idx] & 0x7fffffffu].x;
+    return a.pb_in[col * a.ent_stride + start + idx].x;
+}
+// Phase A: denominators of the thread's pairs; prefix product of pair j parked in pb_out[start + j].x.
+// Only the x coordinates are read unless they coincide (identity operand, doubling or inverse pair), which needs the y's too.
 HD void aff_phase_a(const AffineArgs& a, uint64_t g) {
     uint64_t col; uint32_t start, L;
     Fq acc = fp_one<FqTag>();
     if (aff_thread_chunk(a, g, &col, &start, &L) && L >= 2) {
         const uint32_t K = L >> 1;
         for (uint32_t j = 0; j < K; ++j) {
-            const G1Affine p = aff_input(a, col, start, 2 * j), q = aff_input(a, col, start, 2 * j + 1);
+            const Fq px = aff_input_x(a, col, start, 2 * j), qx = aff_input_x(a, col, start, 2 * j + 1);
             a.pb_out[col * a.ent_stride + start + j].x = acc;
-            acc = acc * aff_denominator(p, q);
+            Fq d = qx - px;
+            if (fp_is_zero(d) || fp_is_zero(px) || fp_is_zero(qx))       // rare: fall back to the complete rule (needs y)
+                d = aff_denominator(aff_input(a, col, start, 2 * j), aff_input(a, col, start, 2 * j + 1));
+            acc = acc * d;
         }
     }
     a.thread_prod[g] = acc;

@@ -47,6 +47,12 @@ def sweep():
 
 if __name__ == "__main__":
     nat.init(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "one":          # one k=17, c=16, batch-60 call after a warm-up (for ncu launch lists)
+        n = 1 << 17
+        bases = dev.DeviceBases(dev.generate_bases(n, seed=3), window_bits=16)
+        sc = dev.random_scalars(n, batch=60, seed=5)
+        print("k=17 c=16 batch=60: %.3f ms" % run(bases, sc, reps=2))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sweep":
         sweep()
         sys.exit(0)
