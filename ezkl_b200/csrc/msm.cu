@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(TREE_THREADS) k_combine_heavy(const uint32_t* 
 
 // 10: sum_b (b+1) * B_b.  Thread t owns buckets [t*M, (t+1)*M): running sums give sum_j (j+1) B and S = sum B;
 //     the block offset (t*M) * S is a small scalar multiple; then a block tree.
-__global__ void __launch_bounds__(TREE_THREADS) k_reduce(const G1Xyzz* __restrict__ bucket_sums, uint32_t nbuckets, G1Xyzz* __restrict__ partials, uint32_t nparts, uint32_t per_thread) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(TREE_THREADS, MIN_CTAS) k_reduce(const G1Xyzz* __restrict__ bucket_sums, uint32_t nbuckets, G1Xyzz* __restrict__ partials, uint32_t nparts, uint32_t per_thread) {
     __shared__ G1Xyzz sh[TREE_THREADS];
     const uint32_t col = blockIdx.y;
     const G1Xyzz* bs = bucket_sums + (size_t)col * nbuckets;
@@ -305,16 +306,11 @@ __global__ void __launch_bounds__(TREE_THREADS) k_reduce(const G1Xyzz* __restric
     G1Xyzz run = g1_xyzz_identity(), acc = g1_xyzz_identity();
     if (lo < nbuckets) {
         const uint32_t hi = min(lo + per_thread, nbuckets);
-        // software-pipelined running sums: acc += run_i and run_{i+1} = run_i + B are independent, so the two group
-        // additions of one iteration overlap (the tail of a small batch is latency-bound, not issue-bound)
-        run = bs[hi - 1];
 #pragma unroll 1
-        for (uint32_t b = hi - 1; b-- > lo;) {
-            const G1Xyzz prev = run;
-            run = g1_add(prev, bs[b]);
-            acc = g1_add(acc, prev);
+        for (uint32_t b = hi; b-- > lo;) {
+            run = g1_add(run, bs[b]);
+            acc = g1_add(acc, run);
         }
-        acc = g1_add(acc, run);
         if (lo > 0) acc = g1_add(acc, g1_mul_small(run, lo));
     }
     acc = block_sum(acc, sh);
@@ -419,7 +415,8 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     if (use_affine && cap > 128) cap = 128;          // the affine tree runs ceil(log2(cap)) rounds: keep it at 7
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
-    const uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
+    uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
+    if (const char* e = getenv("B200_MSM_REDUCE_M")) reduce_m = (uint32_t)atoi(e);
     const uint32_t nparts = div_up(div_up(nb, reduce_m), TREE_THREADS);
 
     // counts region (zeroed every call): hist | cursor | len_hist | len_cursor | heavy
@@ -471,7 +468,9 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     }
     k_combine<<<dim3(div_up(nb, 128), batch), 128, 0, st>>>(chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     k_combine_heavy<<<dim3(32, batch), TREE_THREADS, 0, st>>>(heavy, heavy_stride, chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
-    k_reduce<<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
+    static const int reduce_variant = getenv("B200_MSM_REDUCE2") ? atoi(getenv("B200_MSM_REDUCE2")) : 0;
+    if (reduce_variant) k_reduce<2><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
+    else k_reduce<1><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
     k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
     B200_CUDA(cudaGetLastError());
     return 0;
