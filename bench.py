@@ -92,36 +92,45 @@ def gate_program(m):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed regions run: ONE long-lived `nvidia-smi -lms 100` process (started
+    before the warm-up so its start-up cost is outside the timed region); rows are stamped on arrival and only those that fall
+    inside a marked region are summarised."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device):
         super().__init__(daemon=True)
-        self.device, self.rows, self.stop_flag = device, [], False
+        self.device, self.rows, self.regions, self.proc = device, [], [], None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
+                if len(parts) >= 8:
+                    self.rows.append((time.time(), parts))
+        except Exception:
+            pass
+
+    def mark(self, t0, t1):
+        self.regions.append((t0, t1))
 
     def summary(self):
-        self.stop_flag = True
+        time.sleep(0.15)
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=3)
-        if not self.rows:
+        inside = [r for (ts, r) in self.rows if any(t0 <= ts <= t1 + 0.1 for t0, t1 in self.regions)] or [r for _, r in self.rows]
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[1]) for r in self.rows)
+        sm = sorted(float(r[1]) for r in inside)
         reasons = set()
-        for r in self.rows:
+        for r in inside:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][2]), "power_w_max": max(float(r[3]) for r in inside),
+                "reasons": sorted(reasons), "samples": len(inside)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -322,11 +331,12 @@ def run_b200(args):
         return
 
     # ---- device-resident timing (library-side event profiling OFF: nothing but the kernels in the timed region)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    t_reg0 = time.time()
     l0 = nat.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -334,6 +344,7 @@ def run_b200(args):
         step_device()
     e1.record()
     barrier()
+    sampler.mark(t_reg0, time.time())
     launches = nat.launch_count() - l0
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     # ---- same steps again with per-kernel-class CUDA events (roofline leg; not part of `value`)
@@ -353,10 +364,12 @@ def run_b200(args):
     step_host()
     barrier()
     t0 = time.perf_counter()
+    t_reg0 = time.time()
     for _ in range(e2e_steps):
         h2d, d2h, _ = step_host()
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    sampler.mark(t_reg0, time.time())
     clocks = sampler.summary()
 
     pairs, ntt_elts = count_units(ops, n, tr)
