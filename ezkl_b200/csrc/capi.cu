@@ -2,6 +2,7 @@
 // host<->device staging and the host-side tail (point normalisation).  No CPU fallback lives here: every compute entry
 // point needs an initialised CUDA device and fails with an error code otherwise.
 #include <atomic>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -32,7 +33,12 @@ static std::mutex g_mu;
 static std::unordered_map<uint64_t, MsmTable*> g_tables;
 static uint64_t g_next_handle = 1;
 static NttContext g_ntt;           // guarded by g_mu (plan creation) — plans are immutable afterwards
-static const size_t WS_BUDGET = (size_t)12 << 30;   // device scratch budget per call, for batch splitting
+// device scratch budget per call, for batch splitting (B200_WS_BUDGET_MB overrides it — the tests use that to force the split paths)
+static size_t ws_budget() {
+    static const size_t v = getenv("B200_WS_BUDGET_MB") ? (size_t)atol(getenv("B200_WS_BUDGET_MB")) << 20 : (size_t)12 << 30;
+    return v;
+}
+#define WS_BUDGET (ws_budget())
 
 struct Ctx {
     cudaStream_t stream = nullptr;
@@ -127,8 +133,9 @@ static NttPlan* warm_plan(uint32_t log_n, const Fr& omega, cudaStream_t st) {
 static int ntt_call(Ctx* c, const Fr* src, size_t src_stride, size_t n_in, Fr* tmp, Fr* dst, size_t dst_stride, uint32_t log_n,
                     const Fr& omega, const NttScale& pre, const NttScale& post, int batch, cudaStream_t st) {
     if (log_n < 1 || log_n > 28) { set_error("ntt: log_n = %u out of range [1, 28]", log_n); return -1; }
-    if (!warm_plan(log_n, omega, st)) return -2;
-    int rc = ntt_run(g_ntt, src, src_stride, n_in, tmp, (size_t)1 << log_n, dst, dst_stride, log_n, omega, pre, post, batch, st);
+    NttPlan* plan = warm_plan(log_n, omega, st);         // looked up / built under g_mu; the vector of plans is never touched unlocked
+    if (!plan) return -2;
+    int rc = ntt_run(plan, src, src_stride, n_in, tmp, (size_t)1 << log_n, dst, dst_stride, log_n, omega, pre, post, batch, st);
     if (!rc) g_launches += (uint64_t)ntt_launches_per_run(log_n);
     (void)c;
     return rc;

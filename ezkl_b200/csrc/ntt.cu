@@ -364,14 +364,13 @@ static int launch_pass_v1(PassArgs& a, uint64_t lines, int batch, cudaStream_t s
     return 0;
 }
 
-int ntt_run(NttContext& ctx, const Fr* d_src, size_t src_stride, size_t n_in, Fr* d_tmp, size_t tmp_stride, Fr* d_dst, size_t dst_stride,
+int ntt_run(NttPlan* p, const Fr* d_src, size_t src_stride, size_t n_in, Fr* d_tmp, size_t tmp_stride, Fr* d_dst, size_t dst_stride,
             uint32_t log_n, const Fr& omega, const NttScale& pre, const NttScale& post, int batch, cudaStream_t st) {
     B200_CHECK(log_n >= 1 && log_n <= 28, -1, "ntt: log_n = %u out of range [1, 28]", log_n);
     B200_CHECK(batch > 0 && batch <= 65535, -1, "ntt: batch %d out of range", batch);
     const uint64_t N = 1ull << log_n;
     B200_CHECK(n_in <= N, -1, "ntt: n_in %zu > N", n_in);
-    NttPlan* p = ctx.get(log_n, omega, st);
-    if (!p) return -2;
+    B200_CHECK(p && p->log_n == log_n && fp_eq(p->omega, omega), -1, "ntt: plan does not match (log_n, omega)");
     ProfScope ps(PROF_NTT, st);
     PassArgs a;
     memset(&a, 0, sizeof a);

@@ -32,10 +32,11 @@ struct NttContext {
     void release();
 };
 
+// `plan` = NttContext::get(log_n, omega) obtained by the caller under its own lock (plans are immutable once built).
 // dst[p][j] = post(j) * sum_{i < n_in} pre(i) * src[p][i] * omega^(i j),  j < 2^log_n, for p < batch polynomials.
 // src has n_in <= 2^log_n valid elements per polynomial (rest treated as zero), tmp and dst hold 2^log_n each;
 // dst may alias src (when n_in == 2^log_n and strides match); tmp must not alias either.
-int ntt_run(NttContext& ctx, const Fr* d_src, size_t src_stride, size_t n_in, Fr* d_tmp, size_t tmp_stride, Fr* d_dst, size_t dst_stride,
+int ntt_run(NttPlan* plan, const Fr* d_src, size_t src_stride, size_t n_in, Fr* d_tmp, size_t tmp_stride, Fr* d_dst, size_t dst_stride,
             uint32_t log_n, const Fr& omega, const NttScale& pre, const NttScale& post, int batch, cudaStream_t st);
 int ntt_launches_per_run(uint32_t log_n);
 

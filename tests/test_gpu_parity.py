@@ -525,3 +525,13 @@ def test_g_to_lagrange_reproduces_the_reference_srs_and_downsize():
     # a larger transform against the trapdoor SRS: g_to_lagrange([s^i]G) == [L_i(s)]G
     p2 = h2.ParamsKZG.setup(9, 0x1234567)
     assert np.array_equal(h2.g_to_lagrange(p2.g, 9), p2.g_lagrange)
+
+
+def test_batch_splitting_paths():
+    """The host-buffer MSM / NTT entry points split large batches to bound device scratch; force that path with a 1 MB budget."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B200_WS_BUDGET_MB="1")
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "tests", "split_paths_check.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "split paths OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
