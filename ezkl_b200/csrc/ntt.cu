@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass2(const PassArgs a) {
         const uint32_t q = 1u << (s - 1), p = t & (q - 1), blk = t >> (s - 1);
         const uint32_t base = (blk << (s + 1)) + p;
         Fr x[4];
+        const bool sparse = first && a.first && a.n_in < ((uint64_t)M * a.inner_cnt);      // only the first round of a padded pass 1
         if (first) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -194,15 +195,21 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass2(const PassArgs a) {
             const uint32_t o = (1u << s) - 1u;
             Fr u0 = x[0] + x[2], u2 = x[0] - x[2], u1 = x[1] + x[3], u3 = x[1] - x[3];
             if (s > 0) {
-                if (p) u2 = u2 * sh_get(tlo, thi, o + p);
-                u3 = u3 * sh_get(tlo, thi, o + p + q);
+                // zero-padded inputs (coeff_to_extended: n of 2^ext_k coefficients): most first-round operands are zero,
+                // and whole warps agree on which, so the multiplications are skipped without divergence
+                if (p && !(sparse && fp_is_zero(u2))) u2 = u2 * sh_get(tlo, thi, o + p);
+                if (!(sparse && fp_is_zero(u3))) u3 = u3 * sh_get(tlo, thi, o + p + q);
             }
             x[0] = u0; x[1] = u1; x[2] = u2; x[3] = u3;
         }
         if (two) {     // stage s-1: pairs (0,1) and (2,3), twiddle T_{s-1}[p]
             const uint32_t o = (1u << (s - 1)) - 1u;
             Fr v0 = x[0] + x[1], v1 = x[0] - x[1], v2 = x[2] + x[3], v3 = x[2] - x[3];
-            if (s - 1 > 0 && p) { Fr w = sh_get(tlo, thi, o + p); v1 = v1 * w; v3 = v3 * w; }
+            if (s - 1 > 0 && p) {
+                Fr w = sh_get(tlo, thi, o + p);
+                if (!(sparse && fp_is_zero(v1))) v1 = v1 * w;
+                if (!(sparse && fp_is_zero(v3))) v3 = v3 * w;
+            }
             x[0] = v0; x[1] = v1; x[2] = v2; x[3] = v3;
         }
         if (!last) {
