@@ -203,6 +203,12 @@ int b200_dev_upload(void* d_dst, const void* h_src, size_t bytes) {
     B200_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
+int b200_dev_upload_async(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+    Ctx* c; if (int rc = get_ctx(&c)) return rc;
+    B200_CHECK(d_dst && h_src, -1, "dev_upload_async: null pointer");
+    B200_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, pick_stream(c, stream)));     // truly asynchronous only from pinned memory
+    return 0;
+}
 int b200_dev_download(void* h_dst, const void* d_src, size_t bytes) {
     Ctx* c; if (int rc = get_ctx(&c)) return rc;
     B200_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));

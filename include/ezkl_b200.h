@@ -142,6 +142,9 @@ int b200_quotient_eval_dev(const void* const* d_columns, size_t n_columns, uint3
 int b200_dev_alloc(void** d_ptr, size_t bytes);
 int b200_dev_free(void* d_ptr);
 int b200_dev_upload(void* d_dst, const void* h_src, size_t bytes);
+/* enqueue-only upload on `stream` (NULL = the calling thread's library stream); the host buffer must be pinned (b200_host_alloc)
+ * and stay untouched until the stream reaches the copy: lets a resident-column shim overlap witness uploads with the first commits */
+int b200_dev_upload_async(void* d_dst, const void* h_src, size_t bytes, void* stream);
 int b200_dev_download(void* h_dst, const void* d_src, size_t bytes);
 int b200_host_alloc(void** h_ptr, size_t bytes);      /* pinned */
 int b200_host_free(void* h_ptr);
