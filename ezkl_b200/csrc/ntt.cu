@@ -6,12 +6,16 @@
 // Semantics are best_fft's: natural-order in, natural-order out, out[j] = sum_i a[i] * omega^(i*j); arithmetic is exact,
 // so any factorisation gives the reference's bytes.
 //
-// Factorisation: N = M1 * M2 (* M3), one kernel pass per factor.  Each CTA stages G adjacent "lines" of M elements in
-// shared memory (split into two 16-byte planes so warp accesses are conflict-free), runs a radix-2 DIF network on them,
-// and writes them back bit-reversal-corrected with the inter-pass twiddle omega^(j * i_rest) (two-level table) fused into
-// the store.  Coset pre-scaling (zeta^(i mod 3)), zero padding and the 1/N (and zeta^-(i mod 3)) post-scaling of the
-// extended-domain transforms are fused into the first load / last store.  Algorithmic HBM traffic: 64 B per element per
-// transform; this schedule moves 64 B per element per PASS (2 passes up to 2^20, 3 above).
+// Factorisation: N = M1 * M2 (* M3), M <= 1024, one kernel pass per factor.
+//   k_ntt_pass2 (default): 256-thread CTAs hold 1024 elements; every thread runs TWO stages of the radix-2 DIF network on a
+//     register-resident quad per round, the first round loads global -> registers and the last stores registers -> global
+//     (bit reversal, the inter-pass twiddle omega^(j * i_rest) from a full or two-level table, and the post-scale fused), the
+//     per-stage twiddle table is staged into shared memory with cp.async.bulk (TMA) + mbarrier.
+//   k_ntt_pass (v1): one radix-2 stage per shared-memory round trip; kept for tiny passes and as B200_NTT_V=1.
+// Coset pre-scaling (zeta^(i mod 3)), zero padding and the 1/N (and zeta^-(i mod 3)) post-scaling of the extended-domain
+// transforms are fused into the first load / last store.  Algorithmic HBM traffic: 64 B per element per transform; this
+// schedule moves 64 B per element per PASS (2 passes up to 2^20, 3 above).  The kernels are bound by the 254-bit multiply
+// (10-15 per element), not by HBM: see DESIGN.md §4.3.
 #include <cstdlib>
 #include "ntt.cuh"
 
