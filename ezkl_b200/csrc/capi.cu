@@ -265,6 +265,8 @@ int b200_msm_batch_dev(uint64_t bases, const void* d_scalars, size_t n, size_t s
     MsmTable* t = find_table(bases);
     B200_CHECK(t, -1, "msm: unknown bases handle %llu", (unsigned long long)bases);
     B200_CHECK(d_scalars && d_out_xyzz, -1, "msm: null pointer");
+    B200_CHECK(n <= t->n, -1, "msm: %zu scalars per column, %zu bases registered", n, t->n);
+    B200_CHECK(batch <= 1 || stride >= n, -1, "msm: column stride %zu < column length %zu", stride, n);
     if (batch == 0) return 0;
     cudaStream_t st = pick_stream(c, stream);
     const size_t per_col = msm_workspace_per_column(*t, n);
@@ -523,8 +525,10 @@ int b200_poly_eval_batch(const b200_fr* const* polys, size_t n, const b200_fr* x
     B200_CHECK(polys && x && out, -1, "poly_eval: null pointer");
     if (batch == 0) return 0;
     if (c->stage_a.ensure(sizeof(Fr) * (n ? n : 1) * batch) || c->small.ensure(sizeof(Fr) * batch)) return -2;
-    for (size_t p = 0; p < batch; ++p)
+    for (size_t p = 0; p < batch; ++p) {
+        B200_CHECK(n == 0 || polys[p], -1, "poly_eval: polys[%zu] is null", p);
         if (n) B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + p * n, polys[p], sizeof(Fr) * n, cudaMemcpyHostToDevice, c->stream));
+    }
     if (int rc = b200_poly_eval_batch_dev(c->stage_a.p, n, n, x, batch, c->small.p, nullptr)) return rc;
     B200_CUDA(cudaMemcpyAsync(out, c->small.p, sizeof(Fr) * batch, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));
