@@ -40,7 +40,7 @@ HD G1Xyzz g1_dbl_affine(const G1Affine& p) {
     Fq u = fp_dbl(p.y), v = fp_sqr(u), w = u * v, s = p.x * v;
     Fq xx = fp_sqr(p.x), m = fp_dbl(xx) + xx;
     r.x = fp_sqr(m) - fp_dbl(s);
-    r.y = m * (s - r.x) - w * p.y;
+    r.y = fp_mulsub2(m, s - r.x, w, p.y);
     r.zz = v; r.zzz = w;
     return r;
 }
@@ -52,7 +52,7 @@ HD G1Xyzz g1_dbl(const G1Xyzz& p) {
     Fq u = fp_dbl(p.y), v = fp_sqr(u), w = u * v, s = p.x * v;
     Fq xx = fp_sqr(p.x), m = fp_dbl(xx) + xx;
     r.x = fp_sqr(m) - fp_dbl(s);
-    r.y = m * (s - r.x) - w * p.y;
+    r.y = fp_mulsub2(m, s - r.x, w, p.y);
     r.zz = v * p.zz; r.zzz = w * p.zzz;
     return r;
 }
@@ -69,7 +69,7 @@ HD G1Xyzz g1_add_mixed(const G1Xyzz& a, const G1Affine& q) {
     G1Xyzz o;
     Fq pp = fp_sqr(p), ppp = p * pp, qq = a.x * pp;
     o.x = fp_sqr(r) - ppp - fp_dbl(qq);
-    o.y = r * (qq - o.x) - a.y * ppp;
+    o.y = fp_mulsub2(r, qq - o.x, a.y, ppp);
     o.zz = a.zz * pp; o.zzz = a.zzz * ppp;
     return o;
 }
@@ -86,7 +86,7 @@ HD G1Xyzz g1_add(const G1Xyzz& a, const G1Xyzz& b) {
     G1Xyzz o;
     Fq pp = fp_sqr(p), ppp = p * pp, qq = u1 * pp;
     o.x = fp_sqr(r) - ppp - fp_dbl(qq);
-    o.y = r * (qq - o.x) - s1 * ppp;
+    o.y = fp_mulsub2(r, qq - o.x, s1, ppp);
     o.zz = a.zz * b.zz * pp; o.zzz = a.zzz * b.zzz * ppp;
     return o;
 }
