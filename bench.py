@@ -435,10 +435,10 @@ def run_b200(args):
                      "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes_per_launch), "avg_launch_ms": round(acc_ms / max(acc_cnt, 1), 4),
                      "kernel_share_of_step": round(acc_ms / args.steps / ms_dev, 4) if ms_dev > 0 else None,
-                     "issue_bound": {"what": "bucket additions (XYZZ += affine, 8M+2S = 10.4 multiply-equivalents) per second against the measured "
+                     "issue_bound": {"what": "bucket additions (XYZZ += affine: 6 multiplies + 2 dedicated squarings (0.78 each) + one two-product multiply (1.5) + 7 add/sub = 9.46 multiply-equivalents in IMAD.WIDE work) per second against the measured "
                                              "254-bit multiply ceiling of 67.5 G mulmod/s (profiles/r01_microbench_mulmod.txt)",
                                      "adds_per_s": round(my_msm_cols * n * win / (acc_ms / args.steps * 1e-3), 1) if acc_ms > 0 else None,
-                                     "frac": round(my_msm_cols * n * win * 10.4 / (acc_ms / args.steps * 1e-3) / 67.5e9, 4) if acc_ms > 0 else None},
+                                     "frac": round(my_msm_cols * n * win * 9.46 / (acc_ms / args.steps * 1e-3) / 67.5e9, 4) if acc_ms > 0 else None},
                      "note": "integer-issue bound (254-bit modular arithmetic), not HBM bound: see DESIGN.md"},
         "msm_pairs_per_s": round(pairs / world / (msm_ms * 1e-3), 1) * world if msm_ms > 0 else None,
         "ntt_elts_per_s": round(ntt_elts / world / (ntt_ms * 1e-3), 1) * world if ntt_ms > 0 else None,
