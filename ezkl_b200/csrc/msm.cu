@@ -416,7 +416,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
     uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
-    if (const char* e = getenv("B200_MSM_REDUCE_M")) reduce_m = (uint32_t)atoi(e);
+    if (const char* e = getenv("B200_MSM_REDUCE_M")) { const int v = atoi(e); if (v >= 1 && v <= 4096) reduce_m = (uint32_t)v; }    // tuning override
     const uint32_t nparts = div_up(div_up(nb, reduce_m), TREE_THREADS);
 
     // counts region (zeroed every call): hist | cursor | len_hist | len_cursor | heavy
