@@ -204,3 +204,20 @@ def test_batched_affine_accumulation_bodies_on_host():
                 p = pyref.g1_neg(p)
             acc = pyref.g1_add(acc, p)
         assert H.g1_unwire(out[c]) == acc, (c, int(lens[c]))
+
+
+def test_generated_field_arithmetic_is_verified_and_current(tmp_path):
+    """fp_gen.py executes every emitted PTX instruction list (multiply, add, sub, two-product multiply, squaring) in its own
+    interpreter against bigints; the committed fp_ptx.cuh must be exactly what the generator emits today."""
+    import importlib.util
+    gen_path = os.path.join(ROOT, "ezkl_b200", "csrc", "fp_gen.py")
+    spec = importlib.util.spec_from_file_location("fp_gen", gen_path)
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    for name, mod in gen.FIELDS.items():
+        counts = gen.check(name, mod, trials=300)
+        assert counts[0] == 312 and counts[3] < 2 * counts[0] and counts[4] < counts[0]
+    committed = open(os.path.join(ROOT, "ezkl_b200", "csrc", "fp_ptx.cuh")).read()
+    for name, mod in gen.FIELDS.items():
+        for fn, ins, n_in in (("mul", gen.gen_mul(mod), 2), ("mul2", gen.gen_mul2(mod), 4), ("sqr", gen.gen_sqr(mod), 1)):
+            assert gen.emit_fn("%s_%s_ptx" % (name, fn), ins, n_in) in committed, "%s_%s_ptx is stale: run fp_gen.py" % (name, fn)
