@@ -52,7 +52,9 @@ int b200_profile_enable(int on);
 int b200_profile_read(int cls, double* total_ms, uint64_t* count);
 
 /* ---- SRS bases: ParamsKZG.g / .g_lagrange uploaded once (src/pfsys/srs.rs:30-47 loads them; every commit reuses them).
- *      Registration builds the window-precomputed table on the device.  window_bits = 0 picks it from n. */
+ *      Registration builds the window-precomputed table on the device.  window_bits = 0 picks it from n.
+ *      A handle may be used from any number of threads at once; b200_bases_release (and b200_shutdown, which releases every
+ *      handle) must not run while another thread still has an MSM in flight on that handle (ParamsKZG outlives its commits). */
 int b200_bases_register(const b200_g1_affine* bases, size_t n, int window_bits, uint64_t* handle);
 int b200_bases_register_dev(const void* d_bases, size_t n, int window_bits, uint64_t* handle);
 int b200_bases_release(uint64_t handle);
