@@ -30,7 +30,9 @@ def _load():
 
 
 _lib = None
+_dbg = None
 _inited = False
+DBG_LIB_PATH = os.path.join(_HERE, "libezkl_b200_dbg.so")
 
 
 def lib():
@@ -38,6 +40,16 @@ def lib():
     if _lib is None:
         _lib = _load()
     return _lib
+
+
+def dbg_lib():
+    """Test-only companion library (b200_debug_*: per-layer self tests and microbenchmarks).  The product never loads it."""
+    global _dbg
+    if _dbg is None:
+        if not os.path.exists(DBG_LIB_PATH):
+            raise B200Error("libezkl_b200_dbg.so is not built: run `make -C ezkl_b200/csrc`")
+        _dbg = C.CDLL(DBG_LIB_PATH)
+    return _dbg
 
 
 def check(rc: int):

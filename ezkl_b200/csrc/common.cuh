@@ -45,29 +45,55 @@ struct DevBuf {
 };
 
 // Small host->device parameter blobs (programs, pointer tables, per-call constants) without a stream synchronisation:
-// the blob is copied into a pinned ring and an async H2D copy into the matching slot of a device ring is enqueued on the
-// caller's stream.  Slots are only reused after a full lap, and a lap boundary synchronises the device, so neither the
-// pinned source nor the device copy can be overwritten while a kernel may still read it.
+// the blob is copied into a slot of a pinned ring and an async H2D copy into the matching slot of a device ring is enqueued
+// on the caller's stream, followed by an event.  A slot is reused only after its own event has completed (a host-side wait
+// on that one event — never a device-wide synchronisation), so neither the pinned source nor the device copy can be
+// overwritten while a kernel may still read it.  Not capturable in a CUDA graph (a replay would re-read the pinned slot).
 struct StagingRing {
+    static constexpr size_t SLOT = (size_t)256 << 10;
+    static constexpr int NSLOT = 32;
     uint8_t* h = nullptr;
     uint8_t* d = nullptr;
-    size_t cap = 0, head = 0;
+    cudaEvent_t ev[NSLOT] = {};
+    bool used[NSLOT] = {};
+    int head = 0;
     void* push(const void* src, size_t bytes, cudaStream_t st) {
+        if (bytes > SLOT) return nullptr;                          // caller falls back to its synchronous path
         if (!h) {
-            const size_t want = (size_t)8 << 20;
-            if (cudaMallocHost((void**)&h, want) != cudaSuccess || cudaMalloc((void**)&d, want) != cudaSuccess) { cudaGetLastError(); h = nullptr; return nullptr; }
-            cap = want;
+            if (cudaMallocHost((void**)&h, SLOT * NSLOT) != cudaSuccess || cudaMalloc((void**)&d, SLOT * NSLOT) != cudaSuccess) { cudaGetLastError(); release(); return nullptr; }
+            for (int i = 0; i < NSLOT; ++i) if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { release(); return nullptr; }
         }
-        const size_t need = (bytes + 255) & ~(size_t)255;
-        if (need > cap / 4) return nullptr;                       // caller falls back to its synchronous path
-        if (head + need > cap) { if (cudaDeviceSynchronize() != cudaSuccess) return nullptr; head = 0; }
-        memcpy(h + head, src, bytes);
-        if (cudaMemcpyAsync(d + head, h + head, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
-        void* out = d + head;
-        head += need;
-        return out;
+        const int s = head;
+        head = (head + 1) % NSLOT;
+        if (used[s] && cudaEventSynchronize(ev[s]) != cudaSuccess) return nullptr;
+        memcpy(h + s * SLOT, src, bytes);
+        if (cudaMemcpyAsync(d + s * SLOT, h + s * SLOT, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+        if (cudaEventRecord(ev[s], st) != cudaSuccess) return nullptr;
+        used[s] = true;
+        return d + s * SLOT;
+    }
+    void release() {
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        for (int i = 0; i < NSLOT; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; used[i] = false; }
+        h = d = nullptr; head = 0;
     }
 };
+
+// Process-wide tuning knobs, read from the environment ONCE in b200_init (never on a launch path).
+struct Config {
+    size_t ws_budget_call = 0;      // B200_WS_BUDGET_MB: fixed per-call scratch budget (tests use it to force the batch-split paths); 0 = derive
+    size_t ws_budget_total = (size_t)48 << 30;   // scratch the library may hold across all calling threads of a device
+    int ntt_v1 = 0;                 // B200_NTT_V=1: radix-2 shared-memory pass everywhere
+    int ntt_logg = -1;              // B200_NTT_LOGG
+    int ntt_threads = 0;            // B200_NTT_THREADS (v1 pass)
+    int ntt_nofull = 0;             // B200_NTT_NOFULL: two-level inter-pass twiddles even when the full table exists
+    int msm_reduce_m = 0;           // B200_MSM_REDUCE_M
+    int msm_reduce2 = 0;            // B200_MSM_REDUCE2
+    int msm_affine = -1;            // B200_MSM_AFFINE: 1 forces the batched-affine accumulation, 0 the XYZZ chain, -1 picks by work size
+    int shard_min_logn = 22;        // B200_SHARD_MIN_LOGN: a single transform of at least this size is sharded across the devices
+};
+const Config& config();
 
 // Optional device-side timing of kernel classes with CUDA events on the launching stream (bench.py's roofline leg).
 enum ProfClass { PROF_MSM_ACCUMULATE = 0, PROF_MSM_TOTAL = 1, PROF_NTT = 2, PROF_POLY = 3, PROF_NCLASS = 4 };

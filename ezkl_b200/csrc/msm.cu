@@ -16,7 +16,6 @@
 //  11 k_final           per-column sum of the block partials -> one XYZZ point per column
 // HBM traffic per (scalar, base) pair: 32 B scalar (read twice) + W x 64 B table gathers; the kernel is bound by
 // integer issue (IMAD.WIDE), not HBM — see DESIGN.md §kernels.
-#include <cstdlib>
 #include "msm.cuh"
 
 namespace b200 {
@@ -70,7 +69,7 @@ void msm_table_free(MsmTable* t) {
 // ---------------------------------------------------------------------------------------------------------
 // 1 / 3: digit extraction, histogram and scatter
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, size_t stride, uint32_t n, uint32_t table_n, int c, int W,
+__global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, size_t stride, uint32_t n, uint32_t table_n, uint32_t base_off, int c, int W,
                                                  uint32_t nbuckets, uint32_t* __restrict__ counters /*[col][nbuckets]*/,
                                                  const uint32_t* __restrict__ offs /*[col][nbuckets+1]*/, uint32_t* __restrict__ ents, size_t ent_stride,
                                                  const uint32_t* __restrict__ skew) {
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
             const unsigned act = __ballot_sync(0xffffffffu, nz);
             if (nz && !aggregate) {
                 const uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1u;
-                ent[off[bucket] + atomicAdd(&cnt[bucket], 1u)] = ((uint32_t)w * table_n + i) | (d < 0 ? 0x80000000u : 0u);
+                ent[off[bucket] + atomicAdd(&cnt[bucket], 1u)] = ((uint32_t)w * table_n + base_off + i) | (d < 0 ? 0x80000000u : 0u);
             } else if (nz) {
                 const uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1u;
                 const unsigned peers = __match_any_sync(act, bucket);
@@ -104,7 +103,7 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
                 if (SCATTER) {
                     base = __shfl_sync(peers, base, leader);
                     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-                    ent[off[bucket] + base + rank] = ((uint32_t)w * table_n + i) | (d < 0 ? 0x80000000u : 0u);
+                    ent[off[bucket] + base + rank] = ((uint32_t)w * table_n + base_off + i) | (d < 0 ? 0x80000000u : 0u);
                 }
             }
         }
@@ -399,8 +398,8 @@ size_t msm_workspace_per_column(const MsmTable& t, size_t n) {
     return ents * 4 + chunk_stride * (12 + sizeof(G1Xyzz)) + nb * (sizeof(G1Xyzz) + 24) + 65536;
 }
 
-int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int batch, G1Xyzz* d_out, MsmWorkspace& ws, cudaStream_t st) {
-    B200_CHECK(n <= t.n, -1, "msm: %zu scalars but only %zu bases registered", n, t.n);
+int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int batch, G1Xyzz* d_out, MsmWorkspace& ws, cudaStream_t st, size_t base_off) {
+    B200_CHECK(base_off + n <= t.n, -1, "msm: pairs [%zu, %zu) but only %zu bases registered", base_off, base_off + n, t.n);
     B200_CHECK(batch > 0 && batch <= 65535, -1, "msm: batch %d out of range", batch);
     if (n == 0) {
         B200_CUDA(cudaMemsetAsync(d_out, 0, sizeof(G1Xyzz) * batch, st));
@@ -410,13 +409,14 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const uint32_t nb = 1u << (c - 1);
     const size_t ent_stride = (size_t)n * W;
     B200_CHECK(ent_stride < ((size_t)1 << 32), -1, "msm: n*W too large");
-    static const bool use_affine = getenv("B200_MSM_AFFINE") && atoi(getenv("B200_MSM_AFFINE")) != 0;
+    const Config& cfg = config();
+    const bool use_affine = cfg.msm_affine == 1;
     uint32_t cap = pick_cap(ent_stride * batch);
     if (use_affine && cap > 128) cap = 128;          // the affine tree runs ceil(log2(cap)) rounds: keep it at 7
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
     uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
-    if (const char* e = getenv("B200_MSM_REDUCE_M")) { const int v = atoi(e); if (v >= 1 && v <= 4096) reduce_m = (uint32_t)v; }    // tuning override
+    if (cfg.msm_reduce_m >= 1 && cfg.msm_reduce_m <= 4096) reduce_m = (uint32_t)cfg.msm_reduce_m;    // tuning override
     const uint32_t nparts = div_up(div_up(nb, reduce_m), TREE_THREADS);
 
     // counts region (zeroed every call): hist | cursor | len_hist | len_cursor | heavy
@@ -451,9 +451,9 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     B200_CUDA(cudaMemsetAsync(hist, 0, counts_words * 4, st));
     const unsigned dig_blocks = min(div_up(n, 256), 148u * 8u);
     dim3 gd(dig_blocks, batch);
-    k_digits<false><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, c, W, nb, hist, nullptr, nullptr, 0, nullptr);
+    k_digits<false><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, (uint32_t)base_off, c, W, nb, hist, nullptr, nullptr, 0, nullptr);
     k_scan_buckets<<<batch, 1024, 0, st>>>(hist, offs, chunk_offs, nb, cap, skew);
-    k_digits<true><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, c, W, nb, cursor, offs, ents, ent_stride, skew);
+    k_digits<true><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, (uint32_t)base_off, c, W, nb, cursor, offs, ents, ent_stride, skew);
     k_fill_chunks<<<dim3(div_up(nb, 256), batch), 256, (cap + 1) * 4, st>>>(offs, chunk_offs, nb, cap, chunk_start, chunk_len, chunk_stride, len_hist, heavy, heavy_stride);
     k_len_offsets<<<batch, 32, 0, st>>>(len_hist, len_offs, cap);
     const unsigned ch_blocks = min(div_up(chunk_stride, 256), 148u * 8u);
@@ -468,8 +468,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     }
     k_combine<<<dim3(div_up(nb, 128), batch), 128, 0, st>>>(chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     k_combine_heavy<<<dim3(32, batch), TREE_THREADS, 0, st>>>(heavy, heavy_stride, chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
-    static const int reduce_variant = getenv("B200_MSM_REDUCE2") ? atoi(getenv("B200_MSM_REDUCE2")) : 0;
-    if (reduce_variant) k_reduce<2><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
+    if (cfg.msm_reduce2) k_reduce<2><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
     else k_reduce<1><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
     k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
     B200_CUDA(cudaGetLastError());

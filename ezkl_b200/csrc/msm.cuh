@@ -31,9 +31,10 @@ int msm_affine_host_chunks(const G1Affine* table, const uint32_t* ents, size_t n
 // Builds the table from n affine points already on the device (copied; caller keeps ownership of d_bases).
 int msm_table_build(MsmTable* t, const G1Affine* d_bases, size_t n, int c, cudaStream_t st);
 void msm_table_free(MsmTable* t);
-// out[b] = sum_i scalars[b*stride + i] * P_i   (i < n <= table.n), XYZZ form, one point per column, on device.
+// out[b] = sum_i scalars[b*stride + i] * P_(base_off + i)   (base_off + n <= table.n), XYZZ form, one point per column, on device.
+// base_off > 0 is the base-split MSM: each device takes a contiguous range of the (scalar, base) pairs against its table replica.
 int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int batch, G1Xyzz* d_out,
-            MsmWorkspace& ws, cudaStream_t st);
+            MsmWorkspace& ws, cudaStream_t st, size_t base_off = 0);
 int g1_fixed_base_mul_run(const Fr* d_scalars, size_t n, const G1Affine& base, G1Affine* d_out, cudaStream_t st);
 // out[j] = scale * sum_i omega^(i j) * P_i over G1 (halo2 g_to_lagrange / ParamsKZG::downsize); affine in, affine out
 int g1_fft_run(const G1Affine* d_in, uint32_t log_n, const Fr& omega, const Fr* scale, G1Affine* d_out, DevBuf& scratch, cudaStream_t st);

@@ -34,6 +34,12 @@ struct PassArgs {
     const uint4* tw_staged;      // v2: per-stage twiddles, planar [2][M] (lo plane, hi plane), stage s at offset 2^s - 1
     const Fr* t_full;            // v2: omega^e for every e < N (single-multiply inter-pass twiddle), or null
     NttScale pre, post;
+    // sharded transform (one polynomial split across devices in contiguous natural-order slices of 2^log_slice elements):
+    // element idx of the distributed source / destination lives at peers[idx >> log_slice][idx & (2^log_slice - 1)], reached by
+    // ordinary loads / stores on peer-mapped pointers (NVLink), so the exchange steps of the six-step scheme are fused into the passes
+    uint32_t peer_on, log_slice, block0;
+    const Fr* src_peers[8];
+    Fr* dst_peers[8];
 };
 
 DEV Fr sh_get(const uint4* lo, const uint4* hi, uint32_t i) {
@@ -147,10 +153,12 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass2(const PassArgs a) {
     uint4* dlo = sh; uint4* dhi = sh + total; uint4* tlo = sh + 2 * total; uint4* thi = tlo + M;
     const uint32_t tid = threadIdx.x;                  // blockDim.x == G * Q
     const uint32_t tiles_per_outer = a.inner_cnt >> a.log_g;
-    const uint32_t outer = blockIdx.x / tiles_per_outer, tile = blockIdx.x % tiles_per_outer;
+    const uint32_t bx = blockIdx.x + a.block0;
+    const uint32_t outer = bx / tiles_per_outer, tile = bx % tiles_per_outer;
     const uint32_t inner0 = tile << a.log_g;
     const Fr* src = a.src + (size_t)blockIdx.y * a.src_pstride;
     Fr* dst = a.dst + (size_t)blockIdx.y * a.dst_pstride;
+    const uint64_t slice_mask = (1ull << a.log_slice) - 1ull;
     const uint64_t in_base = (uint64_t)outer * a.in_outer_s + (uint64_t)inner0 * a.in_inner_s;
     const uint64_t out_base = (uint64_t)outer * a.out_outer_s + (uint64_t)inner0 * a.out_inner_s;
 
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass2(const PassArgs a) {
                 const uint64_t idx = in_base + (uint64_t)g * a.in_inner_s + (uint64_t)(base + j * q) * a.in_rs;
                 x[j] = fp_zero<FrTag>();
                 if (idx < a.n_in) {
-                    x[j] = fp_load(src + idx);
+                    x[j] = fp_load(a.peer_on ? a.src_peers[idx >> a.log_slice] + (idx & slice_mask) : src + idx);
                     if (a.first) {
                         if (a.pre.mode == 1) x[j] = x[j] * a.pre.c[0];
                         else if (a.pre.mode == 3) { uint32_t m3 = (uint32_t)(idx % 3); if (m3) x[j] = x[j] * a.pre.c[m3]; }
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass2(const PassArgs a) {
                     if (a.post.mode == 1) v = v * a.post.c[0];
                     else if (a.post.mode == 3) v = v * a.post.c[(uint32_t)(idx % 3)];
                 }
-                fp_store(dst + idx, v);
+                fp_store(a.peer_on ? a.dst_peers[idx >> a.log_slice] + (idx & slice_mask) : dst + idx, v);
             }
         }
         first = false;
@@ -333,21 +341,27 @@ void NttContext::release() {
 
 static int launch_pass_v1(PassArgs& a, uint64_t lines, int batch, cudaStream_t st);
 
-// v2 launch: G lines per CTA chosen so that a CTA holds 1024 elements (256 threads, one quad each; 3 CTAs per SM)
-static int launch_pass(PassArgs& a, uint64_t lines, int batch, cudaStream_t st) {
-    const char* ver = getenv("B200_NTT_V");
-    if (a.logm < 2 || (ver && atoi(ver) == 1)) return launch_pass_v1(a, lines, batch, st);
+// v2 launch geometry: G lines per CTA chosen so that a CTA holds 1024 elements (256 threads, one quad each; 3 CTAs per SM).
+// Returns false when the pass has to take the v1 kernel (tiny passes).
+static bool plan_pass_v2(PassArgs& a, uint64_t lines, int batch, uint32_t* threads, size_t* smem) {
+    const Config& cfg = config();
+    if (a.logm < 2 || cfg.ntt_v1) return false;
     uint32_t log_g = a.logm >= 10 ? 0 : 10 - a.logm;
-    if (const char* e = getenv("B200_NTT_LOGG")) log_g = (uint32_t)atoi(e);
+    if (cfg.ntt_logg >= 0) log_g = (uint32_t)cfg.ntt_logg;
     while (log_g > 0 && ((1u << log_g) > a.inner_cnt || (lines >> log_g) * (uint64_t)batch < 296)) --log_g;
     while (log_g > 0 && (a.logm + log_g > 10)) --log_g;
-    if (a.logm + log_g < 7) return launch_pass_v1(a, lines, batch, st);       // fewer than 32 quads: not worth a CTA
+    if (a.logm + log_g < 7) return false;       // fewer than 32 quads: not worth a CTA
     a.log_g = log_g;
-    const uint32_t threads = 1u << (a.logm + log_g - 2);
-    const size_t smem = (((size_t)1 << (a.logm + log_g)) + ((size_t)1 << a.logm)) * 32;
+    *threads = 1u << (a.logm + log_g - 2);
+    *smem = (((size_t)1 << (a.logm + log_g)) + ((size_t)1 << a.logm)) * 32;
+    return true;
+}
+static int launch_pass(PassArgs& a, uint64_t lines, int batch, cudaStream_t st) {
+    uint32_t threads; size_t smem;
+    if (!plan_pass_v2(a, lines, batch, &threads, &smem)) return launch_pass_v1(a, lines, batch, st);
     B200_CHECK(threads <= 256 && smem <= 200 * 1024, -1, "ntt: pass of 2^%u does not fit a CTA", a.logm);
-    B200_CUDA(cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    dim3 grid((unsigned)(lines >> log_g), (unsigned)batch);
+    B200_CUDA(cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));     // per device, idempotent
+    dim3 grid((unsigned)(lines >> a.log_g), (unsigned)batch);
     k_ntt_pass2<<<grid, threads, smem, st>>>(a);
     B200_CUDA(cudaGetLastError());
     return 0;
@@ -355,24 +369,62 @@ static int launch_pass(PassArgs& a, uint64_t lines, int batch, cudaStream_t st) 
 
 static int launch_pass_v1(PassArgs& a, uint64_t lines, int batch, cudaStream_t st) {
     // lines per CTA: largest G in {4,2,1} that still yields >= 2 CTAs per SM (and fits shared memory)
+    const Config& cfg = config();
     uint32_t log_g = 2;
     while (log_g > 0 && ((1u << log_g) > a.inner_cnt || (lines >> log_g) * (uint64_t)batch < 296)) --log_g;
     while (log_g > 0 && (((size_t)1 << (a.logm + log_g)) + ((size_t)1 << a.logm) / 2) * 32 > 200 * 1024) --log_g;
-    if (const char* e = getenv("B200_NTT_LOGG")) { uint32_t v = (uint32_t)atoi(e); while (v > 0 && (1u << v) > a.inner_cnt) --v; log_g = v; }
+    if (cfg.ntt_logg >= 0) { uint32_t v = (uint32_t)cfg.ntt_logg; while (v > 0 && (1u << v) > a.inner_cnt) --v; log_g = v; }
     a.log_g = log_g;
     const size_t smem = (((size_t)1 << (a.logm + log_g)) + (((size_t)1 << a.logm) >> 1)) * 32;
     const uint32_t nbf = (1u << (a.logm + log_g)) >> 1;
     uint32_t threads = nbf < 32 ? 32 : (nbf > 1024 ? 1024 : nbf);
-    if (const char* e = getenv("B200_NTT_THREADS")) { uint32_t v = (uint32_t)atoi(e); if (v >= 32 && v <= 1024 && v < threads) threads = v; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    if (cfg.ntt_threads >= 32 && cfg.ntt_threads <= 1024 && (uint32_t)cfg.ntt_threads < threads) threads = (uint32_t)cfg.ntt_threads;
+    B200_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));     // per device, idempotent
     dim3 grid((unsigned)(lines >> log_g), (unsigned)batch);
     k_ntt_pass<<<grid, threads, smem, st>>>(a);
     B200_CUDA(cudaGetLastError());
     return 0;
+}
+
+// Geometry of pass `idx` of a plan: which buffer it reads / writes (0 = source, 1 = scratch, 2 = destination), its strides,
+// inter-pass twiddle and how many lines it transforms.  Shared by the single-device and the sharded drivers.
+struct PassRole { int in_buf, out_buf; uint64_t lines; };
+static PassRole fill_pass(const NttPlan* p, int idx, uint64_t n_in, PassArgs& a) {
+    const uint64_t N1 = 1ull << p->logm[0], N2 = 1ull << p->logm[1], N3 = 1ull << p->logm[2], N23 = N2 * N3;
+    a.t_lo = p->d_lo; a.t_hi = p->d_hi; a.lo_bits = p->lo_bits; a.t_full = config().ntt_nofull ? nullptr : p->d_full;
+    a.tw_m = p->d_tw[idx]; a.tw_staged = p->d_staged[idx]; a.logm = p->logm[idx];
+    a.in_outer_s = a.out_outer_s = 0; a.tw_on = 0; a.rest_is_inner = 0; a.tw_mul = 0;
+    PassRole r{0, 2, 1};
+    if (p->npass == 1) {
+        a.inner_cnt = 1; a.in_r_fast = 1; a.in_rs = 1; a.in_inner_s = 0; a.out_rs = 1; a.out_inner_s = 0; a.n_in = n_in; a.first = a.last = 1;
+        return r;
+    }
+    if (p->npass == 2) {
+        if (idx == 0) {      // columns i2 (stride 1), transform over i1 (stride N2); twiddle omega^(j1 * i2)
+            a.inner_cnt = (uint32_t)N2; a.in_r_fast = 0; a.in_rs = N2; a.in_inner_s = 1; a.out_rs = N2; a.out_inner_s = 1; a.n_in = n_in; a.first = 1; a.last = 0;
+            a.tw_on = 1; a.rest_is_inner = 1; a.tw_mul = 1;
+            r = PassRole{0, 1, N2};
+        } else {             // rows j1 (stride N2), transform over i2 (stride 1); X[j1 + N1*j2]
+            a.inner_cnt = (uint32_t)N1; a.in_r_fast = 1; a.in_rs = 1; a.in_inner_s = N2; a.out_rs = N1; a.out_inner_s = 1; a.n_in = ~0ull; a.first = 0; a.last = 1;
+            r = PassRole{1, 2, N1};
+        }
+        return r;
+    }
+    // three passes: i = i1*N2*N3 + i2*N3 + i3  ->  j = j1 + N1*j2 + N1*N2*j3
+    if (idx == 0) {
+        a.inner_cnt = (uint32_t)N23; a.in_r_fast = 0; a.in_rs = N23; a.in_inner_s = 1; a.out_rs = N23; a.out_inner_s = 1; a.n_in = n_in; a.first = 1; a.last = 0;
+        a.tw_on = 1; a.rest_is_inner = 1; a.tw_mul = 1;
+        r = PassRole{0, 1, N23};
+    } else if (idx == 1) {   // in place on scratch: outer j1 (stride N23), inner i3 (stride 1), transform over i2 (stride N3); twiddle omega^(N1*j2*i3)
+        a.inner_cnt = (uint32_t)N3; a.in_r_fast = 0; a.in_rs = N3; a.in_inner_s = 1; a.in_outer_s = N23; a.out_rs = N3; a.out_inner_s = 1; a.out_outer_s = N23;
+        a.n_in = ~0ull; a.first = 0; a.last = 0; a.tw_on = 1; a.rest_is_inner = 1; a.tw_mul = N1;
+        r = PassRole{1, 1, N1 * N3};
+    } else {                 // outer j2 (stride N3), inner j1 (stride N23), transform over i3 (stride 1)
+        a.inner_cnt = (uint32_t)N1; a.in_r_fast = 1; a.in_rs = 1; a.in_inner_s = N23; a.in_outer_s = N3; a.out_rs = N1 * N2; a.out_inner_s = 1; a.out_outer_s = N1;
+        a.n_in = ~0ull; a.first = 0; a.last = 1;
+        r = PassRole{1, 2, N1 * N2};
+    }
+    return r;
 }
 
 int ntt_run(NttPlan* p, const Fr* d_src, size_t src_stride, size_t n_in, Fr* d_tmp, size_t tmp_stride, Fr* d_dst, size_t dst_stride,
@@ -386,47 +438,59 @@ int ntt_run(NttPlan* p, const Fr* d_src, size_t src_stride, size_t n_in, Fr* d_t
     PassArgs a;
     memset(&a, 0, sizeof a);
     a.pre = pre; a.post = post;
-    a.t_lo = p->d_lo; a.t_hi = p->d_hi; a.lo_bits = p->lo_bits; a.t_full = getenv("B200_NTT_NOFULL") ? nullptr : p->d_full;
-    if (p->npass == 1) {
-        a.src = d_src; a.src_pstride = src_stride; a.dst = d_dst; a.dst_pstride = dst_stride;
-        a.logm = p->logm[0]; a.inner_cnt = 1; a.in_r_fast = 1; a.in_rs = 1; a.out_rs = 1; a.n_in = n_in; a.first = a.last = 1;
-        a.tw_m = p->d_tw[0]; a.tw_staged = p->d_staged[0];
-        return launch_pass(a, 1, batch, st);
+    const Fr* bufs[3] = {d_src, d_tmp, d_dst};
+    const size_t strides[3] = {src_stride, tmp_stride, dst_stride};
+    for (int idx = 0; idx < p->npass; ++idx) {
+        const PassRole r = fill_pass(p, idx, n_in, a);
+        a.src = bufs[r.in_buf]; a.src_pstride = strides[r.in_buf];
+        a.dst = const_cast<Fr*>(bufs[r.out_buf]); a.dst_pstride = strides[r.out_buf];
+        if (int rc = launch_pass(a, r.lines, batch, st)) return rc;
     }
-    const uint64_t N1 = 1ull << p->logm[0], N2 = 1ull << p->logm[1], N3 = 1ull << p->logm[2];
-    if (p->npass == 2) {
-        // pass 1: columns i2 (stride 1), transform over i1 (stride N2); twiddle omega^(j1 * i2)
-        a.src = d_src; a.src_pstride = src_stride; a.dst = d_tmp; a.dst_pstride = tmp_stride;
-        a.logm = p->logm[0]; a.inner_cnt = (uint32_t)N2; a.in_r_fast = 0;
-        a.in_rs = N2; a.in_inner_s = 1; a.out_rs = N2; a.out_inner_s = 1; a.n_in = n_in; a.first = 1; a.last = 0;
-        a.tw_on = 1; a.rest_is_inner = 1; a.tw_mul = 1; a.tw_m = p->d_tw[0]; a.tw_staged = p->d_staged[0];
-        if (int rc = launch_pass(a, N2, batch, st)) return rc;
-        // pass 2: rows j1 (stride N2), transform over i2 (stride 1); X[j1 + N1*j2]
-        a.src = d_tmp; a.src_pstride = tmp_stride; a.dst = d_dst; a.dst_pstride = dst_stride;
-        a.logm = p->logm[1]; a.inner_cnt = (uint32_t)N1; a.in_r_fast = 1;
-        a.in_rs = 1; a.in_inner_s = N2; a.out_rs = N1; a.out_inner_s = 1; a.n_in = ~0ull; a.first = 0; a.last = 1;
-        a.tw_on = 0; a.tw_m = p->d_tw[1]; a.tw_staged = p->d_staged[1];
-        return launch_pass(a, N1, batch, st);
+    return 0;
+}
+
+// One transform of 2^log_n elements split across ndev devices in contiguous natural-order slices (slice g on device g, in and
+// out).  Every pass runs on all devices at once, device g taking the g-th share of the pass's CTAs; loads and stores go through
+// the peer tables (NVLink loads / stores inside the butterfly kernel), so the all-to-all exchanges of the six-step scheme never
+// exist as separate copies.  Between passes every stream waits for every other device's pass (events).  plans[g], st[g], ev[g]
+// belong to device dev_ids[g]; the caller has enabled peer access.  dst may alias src; tmp must not alias either.
+int ntt_run_sharded(NttPlan* const* plans, int ndev, const int* dev_ids, const Fr* const* src, Fr* const* tmp, Fr* const* dst, uint32_t log_n, const Fr& omega,
+                    const NttScale& pre, const NttScale& post, uint64_t n_in, cudaStream_t* st, cudaEvent_t* ev) {
+    B200_CHECK(ndev >= 2 && ndev <= 8 && (ndev & (ndev - 1)) == 0, -1, "sharded ntt: device count %d must be 2, 4 or 8", ndev);
+    uint32_t log_d = 0;
+    while ((1 << log_d) < ndev) ++log_d;
+    B200_CHECK(log_n >= 12 && log_n <= 28, -1, "sharded ntt: log_n = %u out of range [12, 28]", log_n);
+    const uint64_t N = 1ull << log_n;
+    B200_CHECK(n_in <= N, -1, "sharded ntt: n_in > N");
+    for (int g = 0; g < ndev; ++g) B200_CHECK(plans[g] && plans[g]->log_n == log_n && fp_eq(plans[g]->omega, omega), -1, "sharded ntt: plan %d does not match", g);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    const Fr* const* bufs_r[3] = {src, tmp, dst};
+    for (int idx = 0; idx < plans[0]->npass; ++idx) {
+        for (int g = 0; g < ndev; ++g) {
+            PassArgs a;
+            memset(&a, 0, sizeof a);
+            a.pre = pre; a.post = post;
+            const PassRole r = fill_pass(plans[g], idx, n_in, a);
+            uint32_t threads; size_t smem;
+            if (!plan_pass_v2(a, r.lines, 1, &threads, &smem) || threads > 256 || smem > 200 * 1024) { cudaSetDevice(cur); set_error("sharded ntt: pass %d of 2^%u is too small to shard", idx, log_n); return -1; }
+            const uint64_t blocks = r.lines >> a.log_g;
+            if (blocks % (uint64_t)ndev) { cudaSetDevice(cur); set_error("sharded ntt: %llu CTAs do not divide over %d devices", (unsigned long long)blocks, ndev); return -1; }
+            a.peer_on = 1; a.log_slice = log_n - log_d; a.block0 = (uint32_t)(blocks / ndev * g);
+            for (int h = 0; h < ndev; ++h) { a.src_peers[h] = bufs_r[r.in_buf][h]; a.dst_peers[h] = const_cast<Fr*>(bufs_r[r.out_buf][h]); }
+            B200_CUDA(cudaSetDevice(dev_ids[g]));
+            B200_CUDA(cudaFuncSetAttribute(k_ntt_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            k_ntt_pass2<<<dim3((unsigned)(blocks / ndev), 1), threads, smem, st[g]>>>(a);
+            B200_CUDA(cudaGetLastError());
+            B200_CUDA(cudaEventRecord(ev[g], st[g]));
+        }
+        for (int g = 0; g < ndev; ++g) {
+            B200_CUDA(cudaSetDevice(dev_ids[g]));
+            for (int h = 0; h < ndev; ++h) if (h != g) B200_CUDA(cudaStreamWaitEvent(st[g], ev[h], 0));
+        }
     }
-    // three passes: i = i1*N2*N3 + i2*N3 + i3  ->  j = j1 + N1*j2 + N1*N2*j3
-    const uint64_t N23 = N2 * N3;
-    a.src = d_src; a.src_pstride = src_stride; a.dst = d_tmp; a.dst_pstride = tmp_stride;
-    a.logm = p->logm[0]; a.inner_cnt = (uint32_t)N23; a.in_r_fast = 0;
-    a.in_rs = N23; a.in_inner_s = 1; a.out_rs = N23; a.out_inner_s = 1; a.n_in = n_in; a.first = 1; a.last = 0;
-    a.tw_on = 1; a.rest_is_inner = 1; a.tw_mul = 1; a.tw_m = p->d_tw[0]; a.tw_staged = p->d_staged[0];
-    if (int rc = launch_pass(a, N23, batch, st)) return rc;
-    // pass 2 (in place on tmp): outer j1 (stride N23), inner i3 (stride 1), transform over i2 (stride N3); twiddle omega^(N1*j2*i3)
-    a.src = d_tmp; a.src_pstride = tmp_stride; a.dst = d_tmp; a.dst_pstride = tmp_stride;
-    a.logm = p->logm[1]; a.inner_cnt = (uint32_t)N3; a.in_r_fast = 0;
-    a.in_rs = N3; a.in_inner_s = 1; a.in_outer_s = N23; a.out_rs = N3; a.out_inner_s = 1; a.out_outer_s = N23; a.n_in = ~0ull; a.first = 0; a.last = 0;
-    a.tw_on = 1; a.rest_is_inner = 1; a.tw_mul = N1; a.tw_m = p->d_tw[1]; a.tw_staged = p->d_staged[1];
-    if (int rc = launch_pass(a, N1 * N3, batch, st)) return rc;
-    // pass 3: outer j2 (stride N3), inner j1 (stride N23), transform over i3 (stride 1)
-    a.src = d_tmp; a.src_pstride = tmp_stride; a.dst = d_dst; a.dst_pstride = dst_stride;
-    a.logm = p->logm[2]; a.inner_cnt = (uint32_t)N1; a.in_r_fast = 1;
-    a.in_rs = 1; a.in_inner_s = N23; a.in_outer_s = N3; a.out_rs = N1 * N2; a.out_inner_s = 1; a.out_outer_s = N1; a.n_in = ~0ull; a.first = 0; a.last = 1;
-    a.tw_on = 0; a.tw_m = p->d_tw[2]; a.tw_staged = p->d_staged[2];
-    return launch_pass(a, N1 * N2, batch, st);
+    B200_CUDA(cudaSetDevice(cur));
+    return 0;
 }
 
 }  // namespace b200

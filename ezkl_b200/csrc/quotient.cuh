@@ -5,12 +5,13 @@
 
 namespace b200 {
 
-// Operand encoding: bits 31..30 = kind (0 slot, 1 constant, 2 column load), bits 29..0 = index.
-enum QSrcKind { QSRC_SLOT = 0, QSRC_CONST = 1, QSRC_LOAD = 2 };
-enum QOp { QOP_ADD = 0, QOP_SUB = 1, QOP_MUL = 2, QOP_NEG = 3, QOP_DOUBLE = 4, QOP_SQUARE = 5, QOP_MOV = 6 };
-static constexpr int Q_MAX_SLOTS = 32;
+// Operand encoding: bits 31..30 = kind (0 slot, 1 constant, 2 column load, 3 the previous instruction's result), bits 29..0 = index.
+enum QSrcKind { QSRC_SLOT = 0, QSRC_CONST = 1, QSRC_LOAD = 2, QSRC_PREV = 3 };
+enum QOp { QOP_ADD = 0, QOP_SUB = 1, QOP_MUL = 2, QOP_NEG = 3, QOP_DOUBLE = 4, QOP_SQUARE = 5, QOP_MOV = 6, QOP_MULADD = 7 };
+static constexpr int Q_MAX_SLOTS = 256;
+static constexpr uint32_t Q_NOSTORE = 0x80000000u;     // op_dst flag: the result is only read as PREV by the next instruction
 
-struct QInstr { uint32_t op_dst; uint32_t a, b; };      // op_dst = op | (dst_slot << 8)
+struct QInstr { uint32_t op_dst; uint32_t a, b, c; };   // op_dst = op | (dst_slot << 8) | NOSTORE;  MULADD: a * b + c
 struct QLoad { uint32_t column; uint32_t offset; };      // element offset already reduced mod 2^ext_k
 
 struct QuotientWorkspace { DevBuf prog; StagingRing ring; };

@@ -16,13 +16,15 @@ import numpy as np
 from . import _native as nat
 from . import fields as F
 
-OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_DOUBLE, OP_SQUARE, OP_MOV = range(7)
-MAX_SLOTS = 32
-_SLOT, _CONST, _LOAD = 0, 1, 2
+OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_DOUBLE, OP_SQUARE, OP_MOV, OP_MULADD = range(8)
+MAX_SLOTS = 256
+NOSTORE = 1 << 31
+_SLOT, _CONST, _LOAD, _PREV = 0, 1, 2, 3
 
 
 class Expression:
-    """Immutable expression node; build with Constant / Query and python operators."""
+    """Immutable expression node; build with Constant / Query and python operators (halo2's Expression<F>: Constant, Fixed /
+    Advice / Instance query at a Rotation, Challenge (a Constant here), Negated, Sum, Product, Scaled)."""
     __slots__ = ("kind", "args")
 
     def __init__(self, kind, *args):
@@ -49,9 +51,6 @@ class Expression:
     def __neg__(self):
         return Expression("negated", self)
 
-    def key(self):
-        return (self.kind,) + tuple(a.key() if isinstance(a, Expression) else a for a in self.args)
-
 
 def Constant(v: int) -> Expression:
     return Expression("constant", v % F.FR_MODULUS)
@@ -67,80 +66,183 @@ def _wrap(o):
 
 
 class QuotientProgram:
-    """Compiled program: loads [(column, rotation)], constants [int], instructions [(op, dst_slot, a, b)]."""
+    """Compiled program: loads [(column, rotation)], constants [int], instructions [(op, dst_slot | NOSTORE, a, b, c)].
+
+    Lowering (what halo2's GraphEvaluator::add_expression does, for the instruction format of include/ezkl_b200.h):
+      * hash-consing — structurally equal sub-expressions become one node (memoised per object, so shared DAGs such as repeated
+        squaring cost O(nodes), not O(tree));
+      * a product whose only use is one operand of a sum becomes a fused multiply-add (GraphEvaluator's Horner steps are exactly these);
+      * evaluation order by register need (the operand that needs more registers first), results in at most 256 slots allocated by
+        last use; a result read only by the next instruction stays in the PREV register and is never stored."""
 
     def __init__(self, expr: Expression):
         self.loads, self.consts, self.instrs = [], [], []
         self._load_ix, self._const_ix = {}, {}
-        nodes, order = {}, []            # key -> (kind, operand keys) in post-order, shared sub-expressions once
+        # ---- 1. hash-consed DAG: node id -> (kind, payload / child ids)
+        by_key, memo, nodes = {}, {}, []
 
-        def visit(e):
-            k = e.key()
-            if k in nodes:
-                return k
+        def intern(kind, payload):
+            key = (kind,) + tuple(payload)
+            if key not in by_key:
+                by_key[key] = len(nodes)
+                nodes.append((kind, tuple(payload)))
+            return by_key[key]
+
+        stack = [(expr, False)]
+        while stack:                                       # iterative post-order: deep Horner chains do not hit the recursion limit
+            e, ready = stack.pop()
+            if id(e) in memo:
+                continue
             if e.kind in ("constant", "query"):
-                nodes[k] = (e.kind, e.args)
+                memo[id(e)] = intern(e.kind, e.args)
+            elif ready:
+                kids = tuple(memo[id(a)] for a in e.args)
+                kind = e.kind
+                if kind == "product" and kids[0] == kids[1]:
+                    kind, kids = "square", (kids[0],)
+                memo[id(e)] = intern(kind, kids)
             else:
-                nodes[k] = (e.kind, tuple(visit(a) for a in e.args))
-                order.append(k)
-            return k
-
-        root = visit(expr)
-        if nodes[root][0] in ("constant", "query"):      # a bare leaf still needs one instruction to produce a row value
-            order.append(("mov", root))
-            nodes[("mov", root)] = ("mov", (root,))
-            root = ("mov", root)
-        last_use = {}
-        for i, k in enumerate(order):
-            for a in nodes[k][1]:
-                last_use[a] = i
-        last_use[root] = len(order)
+                stack.append((e, True))
+                for a in e.args:
+                    if id(a) not in memo:
+                        stack.append((a, False))
+        root = memo[id(expr)]
+        self._keep = expr                                  # ids in `memo` stay valid while the tree is alive
+        leaf = lambda i: nodes[i][0] in ("constant", "query")
+        if leaf(root):                                     # a bare leaf still needs one instruction to produce a row value
+            root = intern("mov", (root,))
+        # ---- 2. reference counts over the reachable DAG, then multiply-add fusion
+        uses = {}
+        seen, order_probe = set(), [root]
+        while order_probe:
+            i = order_probe.pop()
+            if i in seen:
+                continue
+            seen.add(i)
+            for c in (() if leaf(i) else nodes[i][1]):
+                uses[c] = uses.get(c, 0) + 1
+                order_probe.append(c)
+        fused = {}                                         # sum node -> (x, y, addend) with x * y the absorbed product
+        for i in seen:
+            kind, kids = nodes[i]
+            if kind == "sum":
+                for pos in (0, 1):
+                    p = kids[pos]
+                    if nodes[p][0] == "product" and uses.get(p, 0) == 1:
+                        fused[i] = (nodes[p][1][0], nodes[p][1][1], kids[1 - pos])
+                        break
+        operands_of = lambda i: fused[i] if i in fused else nodes[i][1]
+        # ---- 3. register need (Sethi-Ullman on the DAG, shared nodes counted where first met) and evaluation order
+        need = {}
+        order = []
+        work = [(root, False)]
+        done = set()
+        while work:
+            i, ready = work.pop()
+            if i in done or leaf(i):
+                continue
+            ops = [c for c in operands_of(i) if not leaf(c)]
+            if ready:
+                ns = sorted((need.get(c, 0) for c in ops), reverse=True)
+                need[i] = max([n_ + j for j, n_ in enumerate(ns)] + [1])
+                done.add(i)
+                order.append(i)
+            else:
+                work.append((i, True))
+                # children pushed so that the one with the LARGER need is popped (evaluated) first: estimate by subtree depth
+                for c in sorted(ops, key=lambda c_: self._depth(nodes, operands_of, c_, leaf)):
+                    if c not in done:
+                        work.append((c, False))
+        # ---- 4. emission with last-use slot allocation
+        pos_of = {i: p for p, i in enumerate(order)}
+        last_use, use_list = {}, {}
+        for p, i in enumerate(order):
+            for c in operands_of(i):
+                if not leaf(c):
+                    last_use[c] = p
+                    use_list.setdefault(c, []).append(p)
         free, slot_of = list(range(MAX_SLOTS - 1, -1, -1)), {}
 
-        def operand(k):
-            kind, args = nodes[k]
+        def operand(c, p):
+            kind, payload = nodes[c]
             if kind == "constant":
-                if args[0] not in self._const_ix:
-                    self._const_ix[args[0]] = len(self.consts)
-                    self.consts.append(args[0])
-                return (_CONST << 30) | self._const_ix[args[0]]
+                if payload[0] not in self._const_ix:
+                    self._const_ix[payload[0]] = len(self.consts)
+                    self.consts.append(payload[0])
+                return (_CONST << 30) | self._const_ix[payload[0]]
             if kind == "query":
-                if args not in self._load_ix:
-                    self._load_ix[args] = len(self.loads)
-                    self.loads.append(args)
-                return (_LOAD << 30) | self._load_ix[args]
-            return (_SLOT << 30) | slot_of[k]
+                if payload not in self._load_ix:
+                    self._load_ix[payload] = len(self.loads)
+                    self.loads.append(payload)
+                return (_LOAD << 30) | self._load_ix[payload]
+            if pos_of[c] == p - 1:
+                return _PREV << 30
+            return (_SLOT << 30) | slot_of[c]
 
-        opmap = {"sum": OP_ADD, "sub": OP_SUB, "product": OP_MUL, "negated": OP_NEG, "mov": OP_MOV}
-        for i, k in enumerate(order):
-            kind, args = nodes[k]
-            a = operand(args[0])
-            b = operand(args[1]) if len(args) > 1 else 0
-            op = opmap[kind]
-            if kind == "product" and args[0] == args[1]:
-                op, b = OP_SQUARE, 0
-            for x in set(args):                        # operands whose last use is here free their slot before dst is chosen
-                if x in slot_of and last_use.get(x) == i:
-                    free.append(slot_of[x])
-            if not free:
-                raise nat.B200Error("QuotientProgram: more than %d live intermediates" % MAX_SLOTS)
-            dst = free.pop()
-            slot_of[k] = dst
-            self.instrs.append((op, dst, a, b))
+        opmap = {"sum": OP_ADD, "sub": OP_SUB, "product": OP_MUL, "negated": OP_NEG, "mov": OP_MOV, "square": OP_SQUARE}
+        for p, i in enumerate(order):
+            kind, _ = nodes[i]
+            ops = operands_of(i)
+            enc = [operand(c, p) for c in ops] + [0, 0]
+            op = OP_MULADD if i in fused else opmap[kind]
+            for c in set(ops):                             # operands whose last use is here free their slot before dst is chosen
+                if c in slot_of and last_use.get(c) == p:
+                    free.append(slot_of.pop(c))
+            only_next = use_list.get(i) == [p + 1] or (i == root)
+            if only_next:
+                dst = NOSTORE
+            else:
+                if not free:
+                    raise nat.B200Error("QuotientProgram: more than %d live intermediates; split the constraint system into partial sums" % MAX_SLOTS)
+                slot_of[i] = free.pop()
+                dst = slot_of[i]
+            self.instrs.append((op, dst, enc[0], enc[1], enc[2]))
+
+    @staticmethod
+    def _depth(nodes, operands_of, i, leaf, _cache={}):
+        # iterative depth with a per-call cache keyed on the node table identity
+        key = (id(nodes), i)
+        if key in _cache:
+            return _cache[key]
+        stack = [(i, False)]
+        while stack:
+            j, ready = stack.pop()
+            kj = (id(nodes), j)
+            if kj in _cache:
+                continue
+            if leaf(j):
+                _cache[kj] = 0
+                continue
+            kids = operands_of(j)
+            if ready:
+                _cache[kj] = 1 + max(_cache[(id(nodes), c)] for c in kids)
+            else:
+                stack.append((j, True))
+                for c in kids:
+                    if (id(nodes), c) not in _cache:
+                        stack.append((c, False))
+        return _cache[key]
+
+    @property
+    def n_slots(self):
+        return 1 + max([d & 0xFFFF for _, d, *_ in self.instrs if not d & NOSTORE] + [0])
 
     def arrays(self):
         loads = np.array(self.loads, dtype=np.int64).reshape(-1, 2).astype(np.int32)
         consts = np.stack([F.fr_to_limbs(c) for c in self.consts]) if self.consts else np.zeros((0, 4), np.uint64)
-        prog = np.array([[op | (dst << 8), a, b] for op, dst, a, b in self.instrs], dtype=np.uint32).reshape(-1, 3)
+        prog = np.array([[(op | ((dst & 0xFFFF) << 8) | (dst & NOSTORE)), a, b, c] for op, dst, a, b, c in self.instrs], dtype=np.uint32).reshape(-1, 4)
         return np.ascontiguousarray(loads), np.ascontiguousarray(consts), np.ascontiguousarray(prog)
 
     def evaluate_ints(self, column_values, idx: int, n_rows: int, rot_scale: int) -> int:
         """Reference semantics on python ints (used by the tests to cross-check the compiler itself)."""
         r = F.FR_MODULUS
         slots = [0] * MAX_SLOTS
+        prev = 0
 
         def src(s):
             kind, i = s >> 30, s & 0x3FFFFFFF
+            if kind == _PREV:
+                return prev
             if kind == _SLOT:
                 return slots[i]
             if kind == _CONST:
@@ -148,8 +250,7 @@ class QuotientProgram:
             col, rot = self.loads[i]
             return column_values[col][(idx + rot * rot_scale) % n_rows]
 
-        last = 0
-        for op, dst, a, b in self.instrs:
+        for op, dst, a, b, c in self.instrs:
             x = src(a)
             if op == OP_ADD:
                 v = x + src(b)
@@ -157,6 +258,8 @@ class QuotientProgram:
                 v = x - src(b)
             elif op == OP_MUL:
                 v = x * src(b)
+            elif op == OP_MULADD:
+                v = x * src(b) + src(c)
             elif op == OP_NEG:
                 v = -x
             elif op == OP_DOUBLE:
@@ -165,9 +268,10 @@ class QuotientProgram:
                 v = x * x
             else:
                 v = x
-            slots[dst] = v % r
-            last = dst
-        return slots[last]
+            prev = v % r
+            if not dst & NOSTORE:
+                slots[dst] = prev
+        return prev
 
 
 def evaluate_h(program: QuotientProgram, columns, k: int, ext_k: int) -> np.ndarray:

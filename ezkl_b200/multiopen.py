@@ -48,9 +48,11 @@ def evaluate_vanishing_polynomial(roots, z):
     return acc
 
 
-def _horner_scalars(base: int, count: int):
-    """fold(zero, |acc, p| acc * base + p) over `count` polynomials == sum_j base^(count-1-j) * p_j."""
-    return [pow(base, count - 1 - j, R) for j in range(count)]
+def _powers(base: int, count: int):
+    """[1, base, base^2, ...]: SHPLONK combines with `.zip(powers(y))` / `.zip(powers(v))` (UPSTREAM shplonk/prover.rs and
+    shplonk/verifier.rs, PSE halo2 v0.3 lineage) — ASCENDING powers, the first polynomial / rotation set gets the exponent 0.
+    (The descending Horner fold `acc * base + p` is the GWC multiopen's rule, not SHPLONK's.)"""
+    return [pow(base, j, R) for j in range(count)]
 
 
 class ProverQuery:
@@ -95,9 +97,9 @@ def create_proof(params: h2.ParamsKZG, queries, y: int, v: int, u: int):
     one = F.fr_to_limbs(1)
     quotient_polys, set_numerators, set_r = [], [], []
     for points, polys in sets:
-        # N_i(X) = sum_j y^(m-1-j) (P_ij(X) - R_ij(X)),  R_ij = low-degree interpolant of P_ij on the set's points
+        # N_i(X) = sum_j y^j (P_ij(X) - R_ij(X)),  R_ij = low-degree interpolant of P_ij on the set's points
         r_polys = [lagrange_interpolate(list(points), [F.fr_from_limbs(h2.eval_polynomial(p, F.fr_to_limbs(x))) for x in points]) for p in polys]
-        ys = _horner_scalars(y, len(polys))
+        ys = _powers(y, len(polys))
         n_x = h2.poly_lincomb(polys, np.stack([F.fr_to_limbs(s) for s in ys]))
         r_comb = [sum(ys[j] * r_polys[j][t] for j in range(len(polys))) % R for t in range(len(points))]
         n_x = h2.poly_op("sub", n_x, _poly_from_ints(r_comb, n))
@@ -107,7 +109,7 @@ def create_proof(params: h2.ParamsKZG, queries, y: int, v: int, u: int):
         quotient_polys.append(q_x)
         set_numerators.append(n_x)
         set_r.append(r_polys)
-    vs = _horner_scalars(v, len(sets))
+    vs = _powers(v, len(sets))
     vs_w = np.stack([F.fr_to_limbs(s) for s in vs])
     h_x = h2.poly_lincomb(quotient_polys, vs_w)
     h1 = params.commit(h_x)
@@ -116,7 +118,7 @@ def create_proof(params: h2.ParamsKZG, queries, y: int, v: int, u: int):
     for (points, polys), r_polys in zip(sets, set_r):
         diffs = [p for p in super_points if p not in points]
         z_i = evaluate_vanishing_polynomial(diffs, u)
-        ys = _horner_scalars(y, len(polys))
+        ys = _powers(y, len(polys))
         l_x = h2.poly_lincomb(polys, np.stack([F.fr_to_limbs(s) for s in ys]))
         r_at_u = sum(ys[j] * sum(c * pow(u, t, R) for t, c in enumerate(r_polys[j])) for j in range(len(polys))) % R
         l_x = h2.poly_op("sub", l_x, _poly_from_ints([r_at_u], n))
@@ -130,4 +132,4 @@ def create_proof(params: h2.ParamsKZG, queries, y: int, v: int, u: int):
     h2_x = np.concatenate([h2.kate_division(l_x, F.fr_to_limbs(u)), np.zeros((1, 4), np.uint64)])
     h2c = params.commit(h2_x)
     return {"h1": h1, "h2": h2c, "h_x": h_x, "l_x": l_x, "h2_x": h2_x, "must_be_zero": must_be_zero, "sets": sets,
-            "super_points": super_points, "numerators": set_numerators, "one": one}
+            "super_points": super_points, "numerators": set_numerators, "r_polys": set_r, "z_diffs": z_diffs, "one": one}

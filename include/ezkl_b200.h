@@ -14,11 +14,20 @@
  *   - Fr / Fq: 4 x u64 little-endian limbs in Montgomery form, exactly halo2curves' in-memory representation
  *     (zero-copy from &[Fr]).  G1 affine = {x, y} 64 B, identity = (0,0).  G1 Jacobian = {x, y, z} 96 B, identity z = 0.
  *   - every call is synchronous with respect to its host buffers and re-entrant: each calling thread gets its own CUDA
- *     stream and scratch arena (halo2 commits / transforms columns from Rayon worker threads).
+ *     stream and scratch arena per device (halo2 commits / transforms columns from Rayon worker threads).  The scratch
+ *     the library holds is bounded process-wide (B200_WS_TOTAL_MB, default 48 GiB per device, divided among the calling
+ *     threads), released when a calling thread exits and at b200_shutdown, which first waits for calls in flight.
+ *   - a process may own 1, 2, 4 or 8 devices (b200_init_multi).  Host-pointer entry points then use all of them: columns
+ *     of a batch are dealt over the devices, a single MSM is split by base range, a single transform of >= 2^22 elements is
+ *     sharded; one host thread per extra device drives its own PCIe link.  Device-pointer entry points run on the device
+ *     that owns the first device pointer they are given.  Environment overrides are read once, in b200_init.
  *   - MSM results are returned NORMALISED (z = 1, or (0,1,0) for the identity), so bytes are canonical and independent
  *     of accumulation order: what `best_multiexp(..).to_affine()` / `batch_normalize` yields on the CPU prover.
  *   - the *_dev entry points take device pointers (e.g. torch tensors' data_ptr) and a cudaStream_t (NULL = the
- *     calling thread's library stream); they do not synchronise.
+ *     calling thread's library stream); they do not synchronise.  Scratch is per calling thread: a call on a different
+ *     stream than the thread's previous call first waits (cudaStreamWaitEvent) for that call's work, so one thread may
+ *     alternate streams safely; calls that stage host parameters (quotient program, lincomb scalars, cycle constants)
+ *     cannot be captured into a CUDA graph.
  */
 #ifndef EZKL_B200_H
 #define EZKL_B200_H
@@ -39,6 +48,10 @@ typedef struct { b200_fq x, y, zz, zzz; } b200_g1_xyzz; /* device-side partial s
 /* ---- lifecycle: replaces halo2_proofs::icicle::try_load_and_set_backend_device("CUDA") + icicle_runtime::warmup
  *      (/root/reference/src/execute.rs:85-97).  device < 0 keeps the current device (e.g. the one torch selected). */
 int b200_init(int device);
+/* one process driving n_devices = 1, 2, 4 or 8 GPUs (devices 0 .. n-1, NVLink peer access enabled between all pairs): the
+ * `b200_init(int n_devices)` of SURVEY.md §8b; what execute::set_device calls when EZKL_B200_DEVICES > 1. */
+int b200_init_multi(int n_devices);
+int b200_device_count(void);
 void b200_shutdown(void);
 const char* b200_last_error(void);
 int b200_version(void);
@@ -67,6 +80,12 @@ int b200_msm(uint64_t bases, const b200_fr* scalars, size_t n, b200_g1_jac* out)
 int b200_msm_batch(uint64_t bases, const b200_fr* const* scalars, size_t n, size_t batch, b200_g1_jac* out);
 /* device-resident: scalars[b*stride + i]; writes batch un-normalised XYZZ partial sums to d_out */
 int b200_msm_batch_dev(uint64_t bases, const void* d_scalars, size_t n, size_t stride, size_t batch, void* d_out_xyzz, void* stream);
+/* ONE MSM (or `batch` of them) whose (scalar, base) pairs are split across the devices of the process: d_scalar_slices[g] is a
+ * device pointer on device g holding, per column, the pairs [lo_g, hi_g) of the contiguous n / n_devices split (remainder to
+ * the low devices), columns back to back.  Every device runs its range against its table replica, the 128-byte XYZZ partial
+ * sums cross NVLink to device 0 and are added there in device order (the group law has no NCCL reduction); out = normalised
+ * points on the host.  Synchronises. */
+int b200_msm_sharded_dev(uint64_t bases, const void* const* d_scalar_slices, size_t n, size_t batch, b200_g1_jac* out);
 /* out[g] = sum_{j < count} points[g*count + j] (device XYZZ arrays): the local add after an all-gather of per-rank partials */
 int b200_g1_sum_dev(const void* d_points_xyzz, size_t groups, size_t count, void* d_out_xyzz, void* stream);
 /* FFT over G1: out[j] = scale * sum_i omega^(i*j) * in[i], 2^log_n affine points in and out (scale may be NULL = 1).
@@ -99,6 +118,14 @@ int b200_extended_to_coeff(b200_fr* a, uint32_t ext_k, const b200_fr* ext_omega_
 int b200_ntt_dev(const void* d_src, size_t src_stride, size_t n_in, void* d_tmp, void* d_dst, size_t dst_stride, uint32_t log_n,
                  const b200_fr* omega, int pre_mode, const b200_fr* pre, int post_mode, const b200_fr* post, size_t batch, void* stream);
 
+/* ONE transform of 2^log_n elements split across the devices of the process: slice g (2^log_n / n_devices contiguous
+ * natural-order elements) lives on device g, for the source, the scratch and the destination alike (dst may alias src).  All
+ * passes run on all devices at once; the exchange steps of the six-step scheme are peer loads / stores over NVLink inside the
+ * butterfly kernels, not separate copies or collectives.  Same pre / post scaling as b200_ntt_dev; n_in <= 2^log_n valid source
+ * elements.  Enqueued on the calling thread's library stream of every device: b200_sync_all() waits for it. */
+int b200_ntt_sharded_dev(const void* const* d_src_slices, void* const* d_tmp_slices, void* const* d_dst_slices, uint32_t log_n, size_t n_in,
+                         const b200_fr* omega, int pre_mode, const b200_fr* pre, int post_mode, const b200_fr* post);
+
 /* ---- column polynomial ops (halo2 `parallelize` loops; create_proof stages 2-9) ---------------------------------
  * op: 0 add, 1 sub, 2 mul (element-wise), 3 scale (out = a * s), 4 axpy (out = a + s * b).  out may alias a or b. */
 int b200_poly_op(int op, const b200_fr* a, const b200_fr* b, const b200_fr* s, b200_fr* out, size_t n);
@@ -128,12 +155,14 @@ int b200_kate_division_dev(const void* d_a, size_t n, const b200_fr* b, void* d_
 /* ---- quotient numerator: halo2 plonk/evaluation.rs Evaluator::evaluate_h (GraphEvaluator) -------------------------
  * A straight-line program of field operations evaluated once per row of the extended domain:
  *   out[idx] = program(columns[c][(idx + rotation * 2^(ext_k - k)) mod 2^ext_k], constants).
- * Operand encoding (b200_instr.a / .b): bits 31..30 kind — 0 slot (result register, < 32), 1 constants[index],
- * 2 loads[index] — bits 29..0 index.  op_dst = op | (dst_slot << 8); op: 0 add, 1 sub, 2 mul, 3 neg(a), 4 double(a),
- * 5 square(a), 6 mov(a).  The row's result is the destination of the last instruction.  Gates, permutation and lookup terms,
- * l0 / l_last / l_active_row, the identity coset and earlier partial sums are all just columns; y, beta, gamma, theta are
- * constants.  Columns are 2^ext_k elements each. */
-typedef struct { uint32_t op_dst; uint32_t a, b; } b200_instr;
+ * Operand encoding (b200_instr.a / .b / .c): bits 31..30 kind — 0 slot (result register, < 256), 1 constants[index],
+ * 2 loads[index], 3 the result of the previous instruction — bits 29..0 index.  op_dst = op | (dst_slot << 8) | (no_store << 31);
+ * op: 0 add, 1 sub, 2 mul, 3 neg(a), 4 double(a), 5 square(a), 6 mov(a), 7 muladd (a * b + c: one step of GraphEvaluator's Horner
+ * calculation).  no_store marks a result that only the next instruction reads (as operand kind 3).  The row's result is the
+ * result of the last instruction.  Gates, permutation and lookup terms, l0 / l_last / l_active_row, the identity coset and earlier
+ * partial sums are all just columns; y, beta, gamma, theta and the phase challenges are constants.  Columns are 2^ext_k elements
+ * each; the program, its loads and constants must fit 160 KB (split larger constraint systems into partial sums carried as a column). */
+typedef struct { uint32_t op_dst; uint32_t a, b, c; } b200_instr;
 typedef struct { uint32_t column; int32_t rotation; } b200_col_ref;
 int b200_quotient_eval(const b200_fr* const* columns, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_col_ref* loads, size_t n_loads,
                        const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr, b200_fr* out);
@@ -142,6 +171,7 @@ int b200_quotient_eval_dev(const void* const* d_columns, size_t n_columns, uint3
 
 /* ---- device / pinned memory helpers for callers without their own CUDA runtime ---------------------------------- */
 int b200_dev_alloc(void** d_ptr, size_t bytes);
+int b200_dev_alloc_on(int device_slot, void** d_ptr, size_t bytes);   /* multi-device process: allocate on device `device_slot` */
 int b200_dev_free(void* d_ptr);
 int b200_dev_upload(void* d_dst, const void* h_src, size_t bytes);
 /* enqueue-only upload on `stream` (NULL = the calling thread's library stream); the host buffer must be pinned (b200_host_alloc)
@@ -151,6 +181,7 @@ int b200_dev_download(void* h_dst, const void* d_src, size_t bytes);
 int b200_host_alloc(void** h_ptr, size_t bytes);      /* pinned */
 int b200_host_free(void* h_ptr);
 int b200_sync(void);                                   /* the calling thread's library stream */
+int b200_sync_all(void);                               /* ... on every device of the process */
 
 #ifdef __cplusplus
 }

@@ -188,17 +188,49 @@ static void j_to_affine(g1a *r, const g1j *p) {
 }
 static void a_neg(g1a *r, const g1a *p) { r->x = p->x; f_neg(&r->y, &p->y, FQ_M); }
 
-/* ---- tiny thread helper ("parallelize" / multicore::scope restated with pthreads) -------------------- */
+/* ---- thread helper ("parallelize" / multicore::scope restated): a persistent pool, like Rayon's, so that an op does not pay
+ *      for thread creation — run_threads(fn, arg, T) runs fn(arg, tid, T) for tid < T, tid 0 on the caller ---------------- */
 typedef void (*job_fn)(void *arg, int tid, int nthreads);
-typedef struct { job_fn fn; void *arg; int tid, nthreads; } job_t;
-static void *job_tramp(void *p) { job_t *j = (job_t *)p; j->fn(j->arg, j->tid, j->nthreads); return 0; }
+#define POOL_MAX 512
+static pthread_mutex_t pool_call_mu = PTHREAD_MUTEX_INITIALIZER;       /* one parallel region at a time */
+static pthread_mutex_t pool_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t pool_go = PTHREAD_COND_INITIALIZER, pool_done = PTHREAD_COND_INITIALIZER;
+static pthread_t pool_th[POOL_MAX];
+static int pool_size = 0, pool_pending = 0, pool_nthreads = 0;
+static unsigned long pool_gen = 0;
+static job_fn pool_fn; static void *pool_arg;
+static void *pool_main(void *p) {
+    const int id = (int)(long)p;                 /* worker id: runs tid = id + 1 */
+    unsigned long seen = 0;
+    pthread_mutex_lock(&pool_mu);
+    for (;;) {
+        while (pool_gen == seen) pthread_cond_wait(&pool_go, &pool_mu);
+        seen = pool_gen;
+        if (id + 1 < pool_nthreads) {
+            job_fn fn = pool_fn; void *arg = pool_arg; int nt = pool_nthreads;
+            pthread_mutex_unlock(&pool_mu);
+            fn(arg, id + 1, nt);
+            pthread_mutex_lock(&pool_mu);
+            if (--pool_pending == 0) pthread_cond_signal(&pool_done);
+        }
+    }
+    return 0;
+}
 static void run_threads(job_fn fn, void *arg, int nthreads) {
     if (nthreads <= 1) { fn(arg, 0, 1); return; }
-    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
-    job_t *jb = (job_t *)malloc(sizeof(job_t) * nthreads);
-    for (int i = 0; i < nthreads; ++i) { jb[i] = (job_t){fn, arg, i, nthreads}; pthread_create(&th[i], 0, job_tramp, &jb[i]); }
-    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], 0);
-    free(th); free(jb);
+    if (nthreads > POOL_MAX) nthreads = POOL_MAX;
+    pthread_mutex_lock(&pool_call_mu);
+    pthread_mutex_lock(&pool_mu);
+    while (pool_size < nthreads - 1) { pthread_create(&pool_th[pool_size], 0, pool_main, (void *)(long)pool_size); pool_size++; }
+    pool_fn = fn; pool_arg = arg; pool_nthreads = nthreads; pool_pending = nthreads - 1; pool_gen++;
+    pthread_cond_broadcast(&pool_go);
+    pthread_mutex_unlock(&pool_mu);
+    fn(arg, 0, nthreads);
+    pthread_mutex_lock(&pool_mu);
+    while (pool_pending > 0) pthread_cond_wait(&pool_done, &pool_mu);
+    pool_nthreads = 0;
+    pthread_mutex_unlock(&pool_mu);
+    pthread_mutex_unlock(&pool_call_mu);
 }
 
 /* ---- MSM: halo2 arithmetic.rs multiexp_serial / best_multiexp ----------------------------------------- */
@@ -271,7 +303,6 @@ static inline uint32_t bitreverse32(uint32_t n, uint32_t l) {
     for (uint32_t i = 0; i < l; ++i) { r = (r << 1) | (n & 1); n >>= 1; }
     return r;
 }
-typedef struct { fe *a; size_t n; size_t twiddle_chunk; const fe *tw; int depth_left; } fft_rec;
 static void butterfly_level(fe *a, size_t n, size_t twiddle_chunk, const fe *tw) {
     fe *left = a, *right = a + n / 2; fe t;
     t = right[0]; right[0] = left[0]; R_ADD(&left[0], &left[0], &t); R_SUB(&right[0], &right[0], &t);
@@ -280,38 +311,60 @@ static void butterfly_level(fe *a, size_t n, size_t twiddle_chunk, const fe *tw)
         right[i] = left[i]; R_ADD(&left[i], &left[i], &t); R_SUB(&right[i], &right[i], &t);
     }
 }
-static void *fft_rec_run(void *p);
-static void recursive_butterfly(fe *a, size_t n, size_t twiddle_chunk, const fe *tw, int depth_left) {
+static void recursive_butterfly(fe *a, size_t n, size_t twiddle_chunk, const fe *tw) {
     if (n == 2) { fe t = a[1]; a[1] = a[0]; R_ADD(&a[0], &a[0], &t); R_SUB(&a[1], &a[1], &t); return; }
-    if (depth_left > 0) {      /* multicore::join: run the two halves concurrently */
-        fft_rec r = {a + n / 2, n / 2, twiddle_chunk * 2, tw, depth_left - 1};
-        pthread_t th; pthread_create(&th, 0, fft_rec_run, &r);
-        recursive_butterfly(a, n / 2, twiddle_chunk * 2, tw, depth_left - 1);
-        pthread_join(th, 0);
-    } else {
-        recursive_butterfly(a, n / 2, twiddle_chunk * 2, tw, 0);
-        recursive_butterfly(a + n / 2, n / 2, twiddle_chunk * 2, tw, 0);
-    }
+    recursive_butterfly(a, n / 2, twiddle_chunk * 2, tw);
+    recursive_butterfly(a + n / 2, n / 2, twiddle_chunk * 2, tw);
     butterfly_level(a, n, twiddle_chunk, tw);
 }
-static void *fft_rec_run(void *p) { fft_rec *r = (fft_rec *)p; recursive_butterfly(r->a, r->n, r->twiddle_chunk, r->tw, r->depth_left); return 0; }
 static int log2_floor(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
+/* best_fft's three parallel regions: the bit-reversal swap and the twiddle table (both `parallelize` loops upstream) and the
+ * recursion, whose multicore::join tree is unrolled here into its levels: 2^L independent sub-transforms, then for each of the
+ * L levels above them one serial butterfly sweep per tree node, the nodes of a level in parallel — the same work per thread as
+ * join gives (the root sweep of n/2 butterflies is serial upstream too). */
+typedef struct { fe *a; const fe *omega; fe *tw; uint32_t log_n; int phase; int depth; } fft_job;
+static void fft_worker(void *arg, int tid, int nt) {
+    fft_job *j = (fft_job *)arg;
+    const size_t n = (size_t)1 << j->log_n;
+    if (j->phase == 0) {                 /* bit reversal: each k < rk pair is swapped by the thread owning k */
+        size_t chunk = (n + nt - 1) / nt, lo = chunk * tid, hi = lo + chunk; if (hi > n) hi = n;
+        for (size_t k = lo; k < hi; ++k) { size_t rk = bitreverse32((uint32_t)k, j->log_n); if (k < rk) { fe t = j->a[rk]; j->a[rk] = j->a[k]; j->a[k] = t; } }
+    } else if (j->phase == 1) {          /* twiddles omega^i, i < n/2: each thread starts from omega^lo */
+        size_t half = n / 2, chunk = (half + nt - 1) / nt, lo = chunk * tid, hi = lo + chunk; if (hi > half) hi = half;
+        if (lo >= hi) return;
+        fe w; fr_pow_u64(&w, j->omega, (u64)lo);
+        for (size_t i = lo; i < hi; ++i) { j->tw[i] = w; R_MUL(&w, &w, j->omega); }
+    } else if (j->phase == 2) {          /* the 2^depth sub-transforms below the join levels */
+        size_t parts = (size_t)1 << j->depth, sub = n >> j->depth;
+        for (size_t p = tid; p < parts; p += nt) recursive_butterfly(j->a + p * sub, sub, parts, j->tw);
+    } else {                             /* one level of the join tree: 2^depth nodes of size n >> depth */
+        size_t parts = (size_t)1 << j->depth, sub = n >> j->depth;
+        for (size_t p = tid; p < parts; p += nt) butterfly_level(j->a + p * sub, sub, parts, j->tw);
+    }
+}
 static void best_fft(fe *a, const fe *omega, uint32_t log_n, int threads) {
     size_t n = (size_t)1 << log_n;
     if (threads < 1) threads = 1;
     int log_threads = log2_floor(threads);
-    for (size_t k = 0; k < n; ++k) { size_t rk = bitreverse32((uint32_t)k, log_n); if (k < rk) { fe t = a[rk]; a[rk] = a[k]; a[k] = t; } }
     if (n < 2) return;
     fe *tw = (fe *)malloc(sizeof(fe) * (n / 2));
-    fe w = FR_R1;
-    for (size_t i = 0; i < n / 2; ++i) { tw[i] = w; R_MUL(&w, &w, omega); }
-    if ((int)log_n <= log_threads) {
-        size_t chunk = 2, twiddle_chunk = n / 2;
-        for (uint32_t s = 0; s < log_n; ++s) {
-            for (size_t off = 0; off < n; off += chunk) butterfly_level(a + off, chunk, twiddle_chunk, tw);
-            chunk *= 2; twiddle_chunk /= 2;
+    fft_job j = {a, omega, tw, log_n, 0, 0};
+    const int par = n >= 4096 ? threads : 1;
+    run_threads(fft_worker, &j, par);
+    j.phase = 1; run_threads(fft_worker, &j, par);
+    if ((int)log_n <= log_threads || par == 1) {
+        if (par == 1 && (int)log_n > log_threads) recursive_butterfly(a, n, 1, tw);
+        else {
+            size_t chunk = 2, twiddle_chunk = n / 2;
+            for (uint32_t s = 0; s < log_n; ++s) {
+                for (size_t off = 0; off < n; off += chunk) butterfly_level(a + off, chunk, twiddle_chunk, tw);
+                chunk *= 2; twiddle_chunk /= 2;
+            }
         }
-    } else recursive_butterfly(a, n, 1, tw, log_threads);
+    } else {
+        j.phase = 2; j.depth = log_threads; run_threads(fft_worker, &j, 1 << log_threads);
+        for (int d = log_threads - 1; d >= 0; --d) { j.phase = 3; j.depth = d; run_threads(fft_worker, &j, 1 << d); }
+    }
     free(tw);
 }
 
@@ -495,8 +548,9 @@ API void orc_prefix_scan(int is_product, const fe *a, size_t n, const fe *init, 
 /* ---- evaluate_h: the quotient-numerator interpreter (UPSTREAM plonk/evaluation.rs GraphEvaluator::evaluate, restated for the
  * instruction format of include/ezkl_b200.h: b200_instr / b200_col_ref).  Row-parallel over threads like halo2's parallelize. */
 typedef struct { const fe *const *cols; uint32_t k, ext_k; const uint32_t *loads; const fe *consts; const uint32_t *prog; size_t n_instr; fe *out; } qe_job;
-static inline const fe *qe_src(const qe_job *j, uint32_t s, const fe *slots, size_t idx, fe *tmp) {
+static inline const fe *qe_src(const qe_job *j, uint32_t s, const fe *slots, const fe *prev, size_t idx, fe *tmp) {
     uint32_t kind = s >> 30, i = s & 0x3fffffffu;
+    if (kind == 3) return prev;
     if (kind == 0) return &slots[i];
     if (kind == 1) return &j->consts[i];
     uint64_t N = (uint64_t)1 << j->ext_k; int64_t scale = (int64_t)1 << (j->ext_k - j->k);
@@ -508,23 +562,28 @@ static inline const fe *qe_src(const qe_job *j, uint32_t s, const fe *slots, siz
 static void qe_worker(void *arg, int tid, int nt) {
     qe_job *j = (qe_job *)arg;
     size_t N = (size_t)1 << j->ext_k, chunk = (N + nt - 1) / nt, lo = chunk * tid, hi = lo + chunk; if (hi > N) hi = N;
-    fe slots[32], ta, tb;
+    fe slots[256], ta, tb, tc;
     for (size_t idx = lo; idx < hi; ++idx) {
-        uint32_t last = 0;
+        fe prev; memset(&prev, 0, sizeof prev);
         for (size_t pc = 0; pc < j->n_instr; ++pc) {
-            uint32_t op = j->prog[3 * pc] & 0xff, dst = (j->prog[3 * pc] >> 8) & 31;
-            const fe *x = qe_src(j, j->prog[3 * pc + 1], slots, idx, &ta);
+            const uint32_t *in = &j->prog[4 * pc];
+            uint32_t op = in[0] & 0xff, dst = (in[0] >> 8) & 255;
+            const fe *x = qe_src(j, in[1], slots, &prev, idx, &ta);
             fe r;
             if (op <= 2) {
-                const fe *y = qe_src(j, j->prog[3 * pc + 2], slots, idx, &tb);
+                const fe *y = qe_src(j, in[2], slots, &prev, idx, &tb);
                 if (op == 0) R_ADD(&r, x, y); else if (op == 1) R_SUB(&r, x, y); else R_MUL(&r, x, y);
+            } else if (op == 7) {
+                const fe *y = qe_src(j, in[2], slots, &prev, idx, &tb), *z = qe_src(j, in[3], slots, &prev, idx, &tc);
+                fe t; R_MUL(&t, x, y); R_ADD(&r, &t, z);
             } else if (op == 3) f_neg(&r, x, FR_M);
             else if (op == 4) R_ADD(&r, x, x);
             else if (op == 5) R_MUL(&r, x, x);
             else r = *x;
-            slots[dst] = r; last = dst;
+            if (!(in[0] >> 31)) slots[dst] = r;
+            prev = r;
         }
-        if (j->n_instr) j->out[idx] = slots[last]; else memset(&j->out[idx], 0, sizeof(fe));
+        j->out[idx] = prev;
     }
 }
 API void orc_quotient_eval(const fe *const *cols, uint32_t k, uint32_t ext_k, const uint32_t *loads, const fe *consts, const uint32_t *prog, size_t n_instr,

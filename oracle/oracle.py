@@ -246,14 +246,14 @@ def prefix_scan(a, init, product: bool) -> np.ndarray:
 
 
 def quotient_eval(columns, k: int, ext_k: int, loads, consts, prog, threads: int = 1) -> np.ndarray:
-    """columns: list of [2^ext_k,4] arrays; loads int32/uint32 [n,2] (column, rotation); consts [m,4]; prog uint32 [p,3]."""
+    """columns: list of [2^ext_k,4] arrays; loads int32/uint32 [n,2] (column, rotation); consts [m,4]; prog uint32 [p,4] (op_dst, a, b, c)."""
     cols = [_fr(c) for c in columns]
     N = 1 << ext_k
     assert all(c.shape[0] == N for c in cols)
     arr = (C.c_void_p * max(1, len(cols)))(*[c.ctypes.data for c in cols])
     loads = np.ascontiguousarray(np.asarray(loads, dtype=np.int64).astype(np.int32).view(np.uint32).reshape(-1, 2))
     consts = np.ascontiguousarray(np.asarray(consts, dtype=np.uint64).reshape(-1, 4))
-    prog = np.ascontiguousarray(np.asarray(prog, dtype=np.uint32).reshape(-1, 3))
+    prog = np.ascontiguousarray(np.asarray(prog, dtype=np.uint32).reshape(-1, 4))
     out = np.zeros((N, 4), np.uint64)
     lib().orc_quotient_eval(arr, C.c_uint32(k), C.c_uint32(ext_k), loads.ctypes.data_as(C.c_void_p), consts.ctypes.data_as(C.c_void_p),
                             prog.ctypes.data_as(C.c_void_p), C.c_size_t(prog.shape[0]), _p(out), C.c_int(threads))

@@ -46,7 +46,7 @@ def test_compiler_matches_tree_semantics_and_oracle():
     for trial in range(25):
         e = random_expr(rng, ncols, 5)
         prog = ev.QuotientProgram(e)
-        assert all(dst < ev.MAX_SLOTS for _, dst, _, _ in prog.instrs)
+        assert all((dst & 0xFFFF) < ev.MAX_SLOTS for _, dst, *_ in prog.instrs)
         loads, consts, instrs = prog.arrays()
         got = H.fr_list(orc.quotient_eval(cols, k, ext_k, loads, consts, instrs, threads=2))
         for idx in (0, 1, N - 1, rng.randrange(N)):
@@ -61,6 +61,26 @@ def test_compiler_matches_tree_semantics_and_oracle():
         got = H.fr_list(orc.quotient_eval(cols, k, ext_k, loads, consts, instrs))
         assert got[3] == eval_tree(e, cols_int, 3, N, scale)
     assert len(ev.QuotientProgram((q + 1) * (q + 1) - (q + 1)).instrs) == 3      # (q+1) computed once, squared, subtracted
+    # a Horner chain (GraphEvaluator's Horner calculation) lowers to one multiply-add per part, none of them stored
+    y, h = ev.Constant(77), ev.Query(0)
+    for t in range(40):
+        h = h * y + ev.Query(t % ncols, t % 3 - 1)
+    prog = ev.QuotientProgram(h)
+    assert len(prog.instrs) == 40 and all(op == ev.OP_MULADD and dst & ev.NOSTORE for op, dst, *_ in prog.instrs)
+    loads, consts, instrs = prog.arrays()
+    assert H.fr_list(orc.quotient_eval(cols, k, ext_k, loads, consts, instrs))[5] == eval_tree(h, cols_int, 5, N, scale)
+    # shared DAGs cost O(nodes): 200 repeated squarings are 200 instructions (2^200 leaves as a tree)
+    e = ev.Query(2)
+    for _ in range(200):
+        e = e * e
+    assert len(ev.QuotientProgram(e).instrs) == 200
+    # more than 32 live intermediates: 100 independent products kept alive until a final sum tree
+    parts = [ev.Query(i % ncols, i % 5 - 2) * ev.Query((i + 1) % ncols, i % 3) - ev.Constant(i) for i in range(100)]
+    while len(parts) > 1:
+        parts = [parts[i] * parts[i + 1] if i + 1 < len(parts) else parts[i] for i in range(0, len(parts), 2)]
+    prog = ev.QuotientProgram(parts[0])
+    loads, consts, instrs = prog.arrays()
+    assert H.fr_list(orc.quotient_eval(cols, k, ext_k, loads, consts, instrs))[7] == eval_tree(parts[0], cols_int, 7, N, scale)
 
 
 @pytest.mark.gpu
@@ -205,7 +225,7 @@ def test_shplonk_multiopen_flow_with_known_trapdoor():
     z = rng.randrange(R)
     zv = H.fr_wire(z)
     ev = lambda poly: H.fr_unwire(h2.eval_polynomial(poly, zv))
-    vs = [pow(v, len(prf["sets"]) - 1 - i, R) for i in range(len(prf["sets"]))]
+    vs = [pow(v, i, R) for i in range(len(prf["sets"]))]                      # ascending: .zip(powers(v)), as SHPLONK combines
     rhs = 0
     for (points, _), num, vi in zip(prf["sets"], prf["numerators"], vs):
         rhs = (rhs + vi * ev(num) * pow(mo.evaluate_vanishing_polynomial(points, z), -1, R)) % R
@@ -217,3 +237,17 @@ def test_shplonk_multiopen_flow_with_known_trapdoor():
     assert np.array_equal(prf["h1"][:8], orc.g1_scalar_mul(G, H.fr_array([H.fr_unwire(h2.eval_polynomial(prf["h_x"], sv))]))[0])
     lhs = orc.g1_scalar_mul(prf["h2"][:8].reshape(1, 8), H.fr_array([(s - u) % R]))
     assert np.array_equal(lhs[0], params.commit(prf["l_x"])[:8])
+    # VerifierSHPLONK's equation restated in the exponent with the trapdoor (no pairing): with z_i = Z_{T \ S_i}(u) and r_ij the
+    # interpolants, the verifier forms  sum_i v^i (z_i / z_0) sum_j y^j (C_ij - [r_ij(u)] G) - (Z_T(u) / z_0) h1 + u h2  and pairs it
+    # against h2 * [s]:  h2(s) * (s - u) == that combination evaluated at s.  The powers of y and v ascend on both sides.
+    zt = mo.evaluate_vanishing_polynomial(prf["super_points"], u)
+    z0_inv = pow(prf["z_diffs"][0], -1, R)
+    evs = lambda poly: H.fr_unwire(h2.eval_polynomial(poly, sv))
+    outer = 0
+    for i, ((points, polys_i), r_polys, zd) in enumerate(zip(prf["sets"], prf["r_polys"], prf["z_diffs"])):
+        inner = 0
+        for j, (pl, rp) in enumerate(zip(polys_i, r_polys)):
+            r_u = sum(c * pow(u, t, R) for t, c in enumerate(rp)) % R
+            inner = (inner + pow(y, j, R) * (evs(pl) - r_u)) % R
+        outer = (outer + pow(v, i, R) * zd % R * z0_inv % R * inner) % R
+    assert evs(prf["h2_x"]) * (s - u) % R == (outer - zt * z0_inv % R * evs(prf["h_x"])) % R

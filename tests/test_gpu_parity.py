@@ -46,10 +46,10 @@ def test_device_field_ops():
         b = np.stack([H.int_to_limbs(pyref.to_mont(y, mod)) for y in ys])
         for opi, op in enumerate(("add", "sub", "mul")):
             out = np.zeros_like(a)
-            nat.check(L.b200_debug_field_op(fid, opi, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))))
+            nat.check(nat.dbg_lib().b200_debug_field_op(fid, opi, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))))
             assert np.array_equal(out, orc.field_op(field, op, a, b)), (field, op)
         out = np.zeros_like(a)
-        nat.check(L.b200_debug_field_op(fid, 3, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))))
+        nat.check(nat.dbg_lib().b200_debug_field_op(fid, 3, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))))
         assert np.array_equal(out, orc.fr_inv(a) if field == "fr" else orc.fq_inv(a)), field
 
 
@@ -63,21 +63,21 @@ def test_device_group_law():
     A[2] = B[2]
     n = C.c_size_t(128)
     out = np.zeros_like(A)
-    nat.check(L.b200_debug_g1_op(0, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
+    nat.check(nat.dbg_lib().b200_debug_g1_op(0, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
     assert np.array_equal(out, orc.g1_add_affine(A, B))
-    nat.check(L.b200_debug_g1_op(1, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
+    nat.check(nat.dbg_lib().b200_debug_g1_op(1, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
     assert np.array_equal(out, orc.g1_add_affine(A, A))
     K = B.copy()
     ks = [rng.randrange(1 << 20) for _ in range(128)]
     ks[3], ks[4] = 0, 1
     for i, k in enumerate(ks):
         K[i, 0] = k
-    nat.check(L.b200_debug_g1_op(2, nat.ptr(A), nat.ptr(K), nat.ptr(out), n))
+    nat.check(nat.dbg_lib().b200_debug_g1_op(2, nat.ptr(A), nat.ptr(K), nat.ptr(out), n))
     assert np.array_equal(out, orc.g1_scalar_mul(A, H.fr_array(ks)))
-    nat.check(L.b200_debug_g1_op(3, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
+    nat.check(nat.dbg_lib().b200_debug_g1_op(3, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
     assert np.array_equal(out, orc.g1_add_affine(A, orc.g1_add_affine(B, B)))
     out[:] = 1
-    nat.check(L.b200_debug_g1_op(4, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
+    nat.check(nat.dbg_lib().b200_debug_g1_op(4, nat.ptr(A), nat.ptr(B), nat.ptr(out), n))
     assert not out.any()
 
 
@@ -89,7 +89,7 @@ def test_device_digit_recoding():
     for c in (4, 13, 16, 20):
         W = (255 + c - 1) // c
         out = np.zeros((len(xs), W), np.int32)
-        nat.check(L.b200_debug_digits(nat.ptr(s), C.c_size_t(len(xs)), C.c_int(c), out.ctypes.data_as(C.c_void_p)))
+        nat.check(nat.dbg_lib().b200_debug_digits(nat.ptr(s), C.c_size_t(len(xs)), C.c_int(c), out.ctypes.data_as(C.c_void_p)))
         for i, x in enumerate(xs):
             assert sum(int(out[i, w]) << (c * w) for w in range(W)) == x
 

@@ -68,10 +68,10 @@ def test_portable_field_ops_vs_oracle():
         b = np.stack([H.int_to_limbs(pyref.to_mont(y, mod)) for y in ys])
         for opi, op in enumerate(("add", "sub", "mul")):
             out = np.zeros_like(a)
-            assert L.b200_debug_host_field_op(fid, opi, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))) == 0
+            assert nat.dbg_lib().b200_debug_host_field_op(fid, opi, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))) == 0
             assert np.array_equal(out, orc.field_op(field, op, a, b)), (field, op)
         out = np.zeros_like(a)
-        L.b200_debug_host_field_op(fid, 3, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs)))
+        nat.dbg_lib().b200_debug_host_field_op(fid, 3, nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs)))
         assert np.array_equal(out, orc.fr_inv(a) if field == "fr" else orc.fq_inv(a))
 
 
@@ -85,21 +85,21 @@ def test_group_law_vs_oracle_including_degenerate_inputs():
     A[2] = B[2]       # P + P through the mixed-add doubling branch
     n = C.c_size_t(32)
     out = np.zeros_like(A)
-    L.b200_debug_host_g1_op(0, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    nat.dbg_lib().b200_debug_host_g1_op(0, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
     assert np.array_equal(out, orc.g1_add_affine(A, B))
-    L.b200_debug_host_g1_op(1, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    nat.dbg_lib().b200_debug_host_g1_op(1, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
     assert np.array_equal(out, orc.g1_add_affine(A, A))
     K = B.copy()
     ks = [rng.randrange(1 << 20) for _ in range(32)]
     ks[3], ks[4] = 0, 1
     for i, k in enumerate(ks):
         K[i, 0] = k
-    L.b200_debug_host_g1_op(2, nat.ptr(A), nat.ptr(K), nat.ptr(out), n)
+    nat.dbg_lib().b200_debug_host_g1_op(2, nat.ptr(A), nat.ptr(K), nat.ptr(out), n)
     assert np.array_equal(out, orc.g1_scalar_mul(A, H.fr_array(ks)))
-    L.b200_debug_host_g1_op(3, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    nat.dbg_lib().b200_debug_host_g1_op(3, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
     assert np.array_equal(out, orc.g1_add_affine(A, orc.g1_add_affine(B, B)))
     out[:] = 1
-    L.b200_debug_host_g1_op(4, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
+    nat.dbg_lib().b200_debug_host_g1_op(4, nat.ptr(A), nat.ptr(B), nat.ptr(out), n)
     assert not out.any()      # P + (-P) = identity = (0,0)
 
 
@@ -111,7 +111,7 @@ def test_signed_window_recoding(c):
     can = np.stack([H.int_to_limbs(x) for x in xs])
     W = (255 + c - 1) // c
     out = np.zeros((len(xs), W), np.int32)
-    L.b200_debug_digits_host(nat.ptr(can), C.c_size_t(len(xs)), C.c_int(c), out.ctypes.data_as(C.c_void_p))
+    nat.dbg_lib().b200_debug_digits_host(nat.ptr(can), C.c_size_t(len(xs)), C.c_int(c), out.ctypes.data_as(C.c_void_p))
     for i, x in enumerate(xs):
         assert sum(int(out[i, w]) << (c * w) for w in range(W)) == x
         assert all(-(1 << (c - 1)) <= int(d) <= (1 << (c - 1)) for d in out[i])
@@ -152,22 +152,22 @@ def test_bench_reference_arm_prints_contract_json():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
 
 
-def test_experimental_carryless_30bit_multiply_vs_bigint():
-    """fp30.cuh (round-2 candidate): 9 x 30-bit-limb Montgomery multiply with 64-bit column accumulators, host build."""
-    L = nat.lib()
-    P, R30 = pyref.P, 1 << 270
+def test_fp64_pipe_multiplier_vs_bigint():
+    """fd.cuh host build: the 5 x 52-bit-limb Montgomery multiplication whose limb products are split with round-toward-zero
+    FMAs must return a * b * 2^-260 mod N (< 2N, limbs normalised) for both fields, including the extremes of the container."""
+    D = nat.dbg_lib()
     rng = random.Random(3)
-    xs = [rng.randrange(P) for _ in range(400)] + [0, 1, P - 1, 2 * P - 1]
-    ys = [rng.randrange(P) for _ in range(400)] + [P - 1, P - 1, P - 1, 2 * P - 1]
-    lim = lambda v: [(v >> (30 * i)) & 0x3FFFFFFF for i in range(9)]
-    a = np.array([lim(x) for x in xs], dtype=np.uint32)
-    b = np.array([lim(y) for y in ys], dtype=np.uint32)
-    out = np.zeros_like(a)
-    assert L.b200_debug_host_fq30_mul(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(len(xs))) == 0
-    rinv = pow(R30, -1, P)
-    for i, (x, y) in enumerate(zip(xs, ys)):
-        v = sum(int(out[i, j]) << (30 * j) for j in range(9))
-        assert v % P == x * y * rinv % P and v < 2 * P and all(int(out[i, j]) < (1 << 30) for j in range(8))
+    for fid, N in ((0, pyref.R), (1, pyref.P)):
+        xs = [rng.getrandbits(256) for _ in range(500)] + [0, 1, N - 1, (1 << 256) - 1, N, 2 * N - 1]
+        ys = [rng.getrandbits(256) for _ in range(500)] + [N - 1, (1 << 256) - 1, N - 1, (1 << 256) - 1, N, 2 * N - 1]
+        a = np.stack([H.int_to_limbs(x) for x in xs])
+        b = np.stack([H.int_to_limbs(y) for y in ys])
+        out = np.zeros_like(a)
+        assert D.b200_debug_host_fd_mul(C.c_int(fid), nat.ptr(a), nat.ptr(b), nat.ptr(out), C.c_size_t(len(xs))) == 0
+        rinv = pow(1 << 260, -1, N)
+        for i, (x, y) in enumerate(zip(xs, ys)):
+            v = H.limbs_to_int(out[i])
+            assert v % N == x * y * rinv % N and v < 2 * N, (fid, i)
 
 
 def test_batched_affine_accumulation_bodies_on_host():
@@ -194,7 +194,7 @@ def test_batched_affine_accumulation_bodies_on_host():
     starts = np.array(starts, dtype=np.uint32)
     lens = np.array(lens, dtype=np.uint32)
     out = np.zeros((len(lens), 8), np.uint64)
-    assert L.b200_debug_host_affine_chunks(nat.ptr(table), ents.ctypes.data_as(C.c_void_p), C.c_size_t(len(ents)), starts.ctypes.data_as(C.c_void_p),
+    assert nat.dbg_lib().b200_debug_host_affine_chunks(nat.ptr(table), ents.ctypes.data_as(C.c_void_p), C.c_size_t(len(ents)), starts.ctypes.data_as(C.c_void_p),
                                            lens.ctypes.data_as(C.c_void_p), C.c_size_t(len(lens)), nat.ptr(out)) == 0
     for c in range(len(lens)):
         acc = None

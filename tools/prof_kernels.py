@@ -25,7 +25,7 @@ def microbench():
             iters = 2000 if variant != 3 else 200
             blocks = 148 * blocks_per_sm
             ms = C.c_float(0)
-            nat.check(L.b200_debug_bench(variant, iters, blocks, threads, C.byref(ms)))
+            nat.check(nat.dbg_lib().b200_debug_bench(variant, iters, blocks, threads, C.byref(ms)))
             ops = blocks * threads * iters
             print("%-24s threads/SM=%5d  %8.3f ms  %8.2f G op/s" % (names[variant], threads * blocks_per_sm, ms.value, ops / ms.value / 1e6), flush=True)
 
@@ -37,7 +37,7 @@ def pipebench():
         for threads, bps in ((256, 2), (256, 4), (256, 8)):
             iters, blocks = 4000, 148 * bps
             ms = C.c_float(0)
-            nat.check(L.b200_debug_bench_pipe(variant, iters, blocks, threads, C.byref(ms)))
+            nat.check(nat.dbg_lib().b200_debug_bench_pipe(variant, iters, blocks, threads, C.byref(ms)))
             per_iter = 16 if variant == 1 else 8          # PTX ops per thread per iteration (v1: 8 lo/hi pairs = 8 fused wide ops)
             ops = blocks * threads * iters * per_iter
             clk = ms.value * 1e-3 * 1.965e9
