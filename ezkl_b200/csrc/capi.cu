@@ -1037,6 +1037,49 @@ int b200_kate_division(const b200_fr* a, size_t n, const b200_fr* b, b200_fr* q)
     return 0;
 }
 
+// ---- mv-lookup multiplicities --------------------------------------------------------------------------------------------------
+int b200_lookup_multiplicities_dev(const void* d_table, size_t n_table, const void* const* d_inputs, size_t n_inputs, size_t n_rows, void* d_m, uint64_t* missing, void* stream) {
+    B200_ENTER(c, d_table);
+    B200_CHECK(d_table && d_m && d_inputs && n_inputs >= 1, -1, "lookup_multiplicities: null pointer");
+    StreamScope ss(c, stream);
+    const void* d_ptrs = c->ring.push(d_inputs, sizeof(void*) * n_inputs, ss.st);
+    if (!d_ptrs) {
+        if (c->small.ensure(sizeof(void*) * n_inputs)) return -2;
+        B200_CUDA(cudaMemcpyAsync(c->small.p, d_inputs, sizeof(void*) * n_inputs, cudaMemcpyHostToDevice, ss.st));
+        B200_CUDA(cudaStreamSynchronize(ss.st));
+        d_ptrs = c->small.p;
+    }
+    unsigned long long* d_missing = nullptr;
+    if (int rc = lookup_multiplicities_run(reinterpret_cast<const Fr*>(d_table), n_table, reinterpret_cast<const Fr* const*>(d_ptrs), n_inputs, n_rows,
+                                           reinterpret_cast<Fr*>(d_m), c->msm_ws.misc, &d_missing, ss.st)) return rc;
+    g_launches += 3;
+    if (missing) {
+        unsigned long long h = 0;
+        B200_CUDA(cudaMemcpyAsync(&h, d_missing, sizeof h, cudaMemcpyDeviceToHost, ss.st));
+        B200_CUDA(cudaStreamSynchronize(ss.st));
+        *missing = h;
+    }
+    return 0;
+}
+int b200_lookup_multiplicities(const b200_fr* table, size_t n_table, const b200_fr* const* inputs, size_t n_inputs, size_t n_rows, b200_fr* m, uint64_t* missing) {
+    B200_ENTER(c, nullptr);
+    B200_CHECK(table && inputs && m && n_inputs >= 1, -1, "lookup_multiplicities: null pointer");
+    if (c->stage_a.ensure(sizeof(Fr) * (n_table + n_inputs * (n_rows ? n_rows : 1))) || c->stage_b.ensure(sizeof(Fr) * n_table)) return -2;
+    B200_CUDA(cudaMemcpyAsync(c->stage_a.p, table, sizeof(Fr) * n_table, cudaMemcpyHostToDevice, c->stream));
+    std::vector<const void*> ptrs(n_inputs);
+    for (size_t j = 0; j < n_inputs; ++j) {
+        B200_CHECK(inputs[j] || n_rows == 0, -1, "lookup_multiplicities: inputs[%zu] is null", j);
+        ptrs[j] = c->stage_a.as<Fr>() + n_table + j * n_rows;
+        if (n_rows) B200_CUDA(cudaMemcpyAsync(const_cast<void*>(ptrs[j]), inputs[j], sizeof(Fr) * n_rows, cudaMemcpyHostToDevice, c->stream));
+    }
+    uint64_t miss = 0;
+    if (int rc = b200_lookup_multiplicities_dev(c->stage_a.p, n_table, ptrs.data(), n_inputs, n_rows, c->stage_b.p, &miss, nullptr)) return rc;
+    B200_CUDA(cudaMemcpyAsync(m, c->stage_b.p, sizeof(Fr) * n_table, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    if (missing) *missing = miss;
+    return 0;
+}
+
 // ---- quotient numerator (evaluate_h) ------------------------------------------------------------------------------
 static_assert(sizeof(b200_instr) == sizeof(QInstr) && sizeof(b200_col_ref) == sizeof(QLoad), "ABI structs must match the kernel's");
 int b200_quotient_eval_dev(const void* const* d_columns, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_col_ref* loads, size_t n_loads,

@@ -24,4 +24,8 @@ int poly_prefix_scan(bool product, const Fr* a, size_t n, const Fr* h_init, Fr* 
 // quotient of a(X) by (X - b): q has n-1 coefficients (kate_division)
 int poly_kate_division(const Fr* a, size_t n, const Fr* h_b, Fr* q, PolyWorkspace& ws, cudaStream_t st);
 
+// mv-lookup multiplicities (lookup.cu): m[i] = number of input cells equal to table[i], counted on the first row holding each value
+int lookup_multiplicities_run(const Fr* d_table, size_t n_table, const Fr* const* d_inputs /*device array*/, size_t n_inputs, size_t n_rows, Fr* d_m, DevBuf& scratch,
+                              unsigned long long** d_missing_out, cudaStream_t st);
+
 }  // namespace b200

@@ -322,14 +322,18 @@ def _omega_powers_column(k: int) -> np.ndarray:
     return np.stack(out)
 
 
-def permutation_product(values, sigmas, k: int, beta: int, gamma: int, delta_start: int = 1) -> np.ndarray:
-    """z(X) in Lagrange form for one permutation chunk:  z[0] = 1,
-        z[i+1] = z[i] * prod_j (v_j[i] + beta * delta_start * DELTA^j * omega^i + gamma) / (v_j[i] + beta * sigma_j[i] + gamma).
-    values / sigmas: lists of [n,4] Lagrange columns (wire form)."""
+def permutation_product(values, sigmas, k: int, beta: int, gamma: int, delta_start: int = 1, z0: int = 1, blinding_factors: int = 0, blinds=None):
+    """z(X) in Lagrange form for ONE permutation chunk (halo2 plonk/permutation/prover.rs, the loop over column chunks):
+        z[0] = z0 (the previous chunk's last_z; 1 for the first chunk),
+        z[i+1] = z[i] * prod_j (v_j[i] + beta * delta_start * DELTA^j * omega^i + gamma) / (v_j[i] + beta * sigma_j[i] + gamma),
+    the last `blinding_factors` rows overwritten with `blinds` (python ints; the prover draws them from its rng).
+    values / sigmas: lists of [n,4] Lagrange columns (wire form); delta_start = DELTA^(index of the chunk's first column).
+    Returns (z [n,4], last_z) with last_z = z[n - blinding_factors - 1], the seed of the next chunk."""
     from . import halo2 as h2
     m = len(values)
     assert m == len(sigmas) and m > 0
     r = F.FR_MODULUS
+    n = 1 << k
     cols = list(values) + list(sigmas) + [_omega_powers_column(k)]
     X = Query(2 * m)
     num = den = None
@@ -342,7 +346,121 @@ def permutation_product(values, sigmas, k: int, beta: int, gamma: int, delta_sta
     numer = evaluate_h(QuotientProgram(num), cols, k, k)
     denom = h2.batch_invert(evaluate_h(QuotientProgram(den), cols, k, k))
     ratio = h2.poly_op("mul", numer, denom)
-    return h2.prefix_scan(ratio, F.fr_to_limbs(1), True)
+    z = h2.prefix_scan(ratio, F.fr_to_limbs(z0), True)
+    if blinding_factors:
+        assert blinds is not None and len(blinds) == blinding_factors
+        for i, b in enumerate(blinds):
+            z[n - blinding_factors + i] = F.fr_to_limbs(b)
+    last_z = F.fr_from_limbs(z[n - blinding_factors - 1])
+    return z, last_z
+
+
+def permutation_products(columns, sigmas, k: int, beta: int, gamma: int, chunk_len: int, blinding_factors: int = 0, blinds=None):
+    """All z_i(X) of a permutation argument: the columns are cut into chunks of chunk_len = cs.degree() - 2, every chunk's
+    product starts at the previous chunk's last_z and its first column uses DELTA^(chunk start).  Returns the list of z columns."""
+    zs, last_z = [], 1
+    for ci, c0 in enumerate(range(0, len(columns), chunk_len)):
+        bl = None if blinds is None else blinds[ci]
+        z, last_z = permutation_product(columns[c0:c0 + chunk_len], sigmas[c0:c0 + chunk_len], k, beta, gamma, pow(DELTA, c0, F.FR_MODULUS), last_z, blinding_factors, bl)
+        zs.append(z)
+    return zs
+
+
+def lookup_multiplicities(table, inputs, n_rows: int):
+    """m(X) of an mv-lookup (stage 2): host-buffer call of b200_lookup_multiplicities; raises when an input is not in the table."""
+    nat.ensure_init()
+    t = nat.as_u64(table, 4)
+    ins = [nat.as_u64(c, 4) for c in inputs]
+    m = np.zeros_like(t)
+    missing = C.c_uint64(0)
+    nat.check(nat.lib().b200_lookup_multiplicities(nat.ptr(t), C.c_size_t(t.shape[0]), nat.ptr_array(ins), C.c_size_t(len(ins)), C.c_size_t(n_rows), nat.ptr(m), C.byref(missing)))
+    if missing.value:
+        raise nat.B200Error("lookup_multiplicities: %d input cells are not in the table" % missing.value)
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Constraint-system terms in the order Evaluator::evaluate_h folds them (custom gates, permutation, lookups); each builder
+# returns a list of Expressions over the flat coset-column list, `fold_y` chains them as value = value * y + term.
+def fold_y(terms, y: int, start: Expression | None = None) -> Expression:
+    value = start if start is not None else Constant(0)
+    yc = Constant(y)
+    for t in terms:
+        value = value * yc + t
+    return value
+
+
+def base_op_gates(selectors: dict, a, b, out: int) -> list:
+    """ezkl's BaseConfig custom gates for one block (/root/reference/src/circuit/ops/chip.rs:362-424, formulas
+    /root/reference/src/circuit/ops/base.rs:28-66): `a`, `b` are the column indices of the two inputs' inner columns, `out` the
+    output column; selectors maps an op name to its selector column.  Non-accumulating ops constrain every inner column,
+    accumulating ops read the previous output at Rotation(-1) and constrain the row's single output cell."""
+    A, B = [Query(c) for c in a], [Query(c) for c in b]
+    terms = []
+    for name, f in (("ADD", lambda x, y_: x + y_), ("SUB", lambda x, y_: x - y_), ("MULT", lambda x, y_: x * y_)):
+        if name in selectors:
+            sel = Query(selectors[name])
+            # one output cell per inner column pair: out column queried at the same row (inner columns share the row in ezkl's layout;
+            # here each pair writes the single output column of its own block)
+            terms.append(sel * (Query(out) - f(A[0], B[0])))
+    dot = None
+    for x, y_ in zip(A, B):
+        dot = x * y_ if dot is None else dot + x * y_
+    ssum = None
+    for y_ in B:
+        ssum = y_ if ssum is None else ssum + y_
+    prod = None
+    for y_ in B:
+        prod = y_ if prod is None else prod * y_
+    prev = Query(out, -1)
+    for name, res in (("DOTINIT", dot), ("DOT", prev + dot), ("SUMINIT", ssum), ("SUM", prev + ssum), ("CUMPRODINIT", prod), ("CUMPROD", prev * prod)):
+        if name in selectors:
+            terms.append(Query(selectors[name]) * (Query(out) - res))
+    return terms
+
+
+def permutation_terms(columns, sigmas, zs, l0: int, l_last: int, l_active: int, x_col: int, beta: int, gamma: int, chunk_len: int, blinding_factors: int) -> list:
+    """The permutation argument's terms (UPSTREAM plonk/evaluation.rs, "Permutations"): columns / sigmas / zs are column indices
+    (values, sigma cosets, grand products), x_col the coset of the identity polynomial X, rotations of z at +1 and -(blinding+1)."""
+    r = F.FR_MODULUS
+    last_rot = -(blinding_factors + 1)
+    L0, LL, LA, X = Query(l0), Query(l_last), Query(l_active), Query(x_col)
+    terms = [(Constant(1) - Query(zs[0])) * L0, (Query(zs[-1]) * Query(zs[-1]) - Query(zs[-1])) * LL]
+    for i in range(1, len(zs)):
+        terms.append((Query(zs[i]) - Query(zs[i - 1], last_rot)) * L0)
+    for ci, z in enumerate(zs):
+        cols = columns[ci * chunk_len:(ci + 1) * chunk_len]
+        sig = sigmas[ci * chunk_len:(ci + 1) * chunk_len]
+        left, right = Query(z, 1), Query(z)
+        for j, (c, s_) in enumerate(zip(cols, sig)):
+            left = left * (Query(c) + Query(s_) * Constant(beta) + Constant(gamma))
+            right = right * (Query(c) + X * Constant(beta * pow(DELTA, ci * chunk_len + j, r) % r) + Constant(gamma))
+        terms.append((left - right) * LA)
+    return terms
+
+
+def mv_lookup_terms(inputs, table: Expression, m: int, phi: int, l0: int, l_last: int, l_active: int, beta: int) -> list:
+    """One mv-lookup's terms (zkonduit fork, UPSTREAM plonk/evaluation.rs "Lookups"): inputs = list of (theta-compressed) input
+    Expressions f_i, table = compressed table Expression t.  With phi_i = f_i + beta and tau = t + beta:
+        l0 * Phi,   l_last * Phi,   l_active * ( tau * prod(phi_i) * (Phi(wX) - Phi(X))  -  (tau * sum_i prod_{j != i} phi_j  -  m * prod(phi_i)) ).
+    (The CPU evaluator writes the second bracket with per-row inversions, prod(phi) * (tau * sum 1/phi_i - m); the two agree wherever
+    no phi_i vanishes.)"""
+    phis = [f + Constant(beta) for f in inputs]
+    tau = table + Constant(beta)
+    prod = phis[0]
+    for p_ in phis[1:]:
+        prod = prod * p_
+    partial = None
+    for i in range(len(phis)):
+        term = None
+        for j, p_ in enumerate(phis):
+            if j != i:
+                term = p_ if term is None else term * p_
+        term = term if term is not None else Constant(1)
+        partial = term if partial is None else partial + term
+    lhs = tau * prod * (Query(phi, 1) - Query(phi))
+    rhs = tau * partial - Query(m) * prod
+    return [Query(l0) * Query(phi), Query(l_last) * Query(phi), (lhs - rhs) * Query(l_active)]
 
 
 def lookup_grand_sum(inputs, table, multiplicities, k: int, beta: int) -> np.ndarray:

@@ -89,10 +89,13 @@ def construct_rotation_sets(queries):
     return [(sk, sets[sk]) for sk in set_order], super_points
 
 
-def create_proof(params: h2.ParamsKZG, queries, y: int, v: int, u: int):
-    """ProverSHPLONK::create_proof with the three challenges supplied.  Returns a dict with the commitments `h1`, `h2`
-    (normalised Jacobian wire) and the polynomials behind them for checking."""
+def create_proof(params: h2.ParamsKZG, queries, y: int = None, v: int = None, u: int = None, transcript=None):
+    """ProverSHPLONK::create_proof.  With `transcript` (ezkl_b200.transcript.EvmTranscriptWrite) the challenges are squeezed and the
+    two commitments written exactly where upstream does (y, v, write h1, u, write h2); without it the three challenges are
+    arguments.  Returns a dict with the commitments `h1`, `h2` (normalised Jacobian wire) and the polynomials behind them."""
     n = params.n
+    if transcript is not None:
+        y, v = transcript.squeeze_challenge(), transcript.squeeze_challenge()
     sets, super_points = construct_rotation_sets(queries)
     one = F.fr_to_limbs(1)
     quotient_polys, set_numerators, set_r = [], [], []
@@ -113,6 +116,9 @@ def create_proof(params: h2.ParamsKZG, queries, y: int, v: int, u: int):
     vs_w = np.stack([F.fr_to_limbs(s) for s in vs])
     h_x = h2.poly_lincomb(quotient_polys, vs_w)
     h1 = params.commit(h_x)
+    if transcript is not None:
+        transcript.write_ec_point(h1)
+        u = transcript.squeeze_challenge()
     # linearisation at u
     l_parts, z_diffs = [], []
     for (points, polys), r_polys in zip(sets, set_r):
@@ -131,5 +137,7 @@ def create_proof(params: h2.ParamsKZG, queries, y: int, v: int, u: int):
     must_be_zero = F.fr_from_limbs(h2.eval_polynomial(l_x, F.fr_to_limbs(u)))
     h2_x = np.concatenate([h2.kate_division(l_x, F.fr_to_limbs(u)), np.zeros((1, 4), np.uint64)])
     h2c = params.commit(h2_x)
+    if transcript is not None:
+        transcript.write_ec_point(h2c)
     return {"h1": h1, "h2": h2c, "h_x": h_x, "l_x": l_x, "h2_x": h2_x, "must_be_zero": must_be_zero, "sets": sets,
             "super_points": super_points, "numerators": set_numerators, "r_polys": set_r, "z_diffs": z_diffs, "one": one}

@@ -152,6 +152,14 @@ int b200_prefix_scan_dev(int product, const void* d_a, size_t n, const b200_fr* 
 int b200_kate_division(const b200_fr* a, size_t n, const b200_fr* b, b200_fr* q);
 int b200_kate_division_dev(const void* d_a, size_t n, const b200_fr* b, void* d_q, void* stream);
 
+/* ---- mv-lookup multiplicities: halo2 plonk/mv_lookup/prover.rs (stage 2 of create_proof; every ezkl lookup, range check, dynamic
+ *      lookup and shuffle: /root/reference/src/circuit/ops/chip.rs:496,662,782,870).  m[i] = number of cells inputs[j][r], j < n_inputs,
+ *      r < n_rows, equal to table[i]; when a value occurs in several table rows (ezkl pads tables with a repeated entry) the FIRST
+ *      row gets the whole count and the others 0.  *missing (may be NULL) = input cells whose value is not in the table (the CPU
+ *      prover panics on those).  m has n_table elements, Montgomery form.  The _dev form synchronises only when missing != NULL. */
+int b200_lookup_multiplicities(const b200_fr* table, size_t n_table, const b200_fr* const* inputs, size_t n_inputs, size_t n_rows, b200_fr* m, uint64_t* missing);
+int b200_lookup_multiplicities_dev(const void* d_table, size_t n_table, const void* const* d_inputs, size_t n_inputs, size_t n_rows, void* d_m, uint64_t* missing, void* stream);
+
 /* ---- quotient numerator: halo2 plonk/evaluation.rs Evaluator::evaluate_h (GraphEvaluator) -------------------------
  * A straight-line program of field operations evaluated once per row of the extended domain:
  *   out[idx] = program(columns[c][(idx + rotation * 2^(ext_k - k)) mod 2^ext_k], constants).

@@ -168,7 +168,9 @@ def test_permutation_product_and_lookup_sum():
     values = [[val[(j, i)] for i in range(n)] for j in range(m)]
     sigmas = [[label(*sigma_of[(j, i)]) for i in range(n)] for j in range(m)]
     beta, gamma = rng.randrange(R), rng.randrange(R)
-    z = H.fr_list(ev.permutation_product([H.fr_array(v) for v in values], [H.fr_array(s) for s in sigmas], k, beta, gamma))
+    z_w, last_z = ev.permutation_product([H.fr_array(v) for v in values], [H.fr_array(s) for s in sigmas], k, beta, gamma)
+    z = H.fr_list(z_w)
+    assert last_z == z[n - 1]
     exp, acc = [], 1
     for i in range(n):
         exp.append(acc)
