@@ -522,7 +522,7 @@ def run_b200(args):
         step_device()
     barrier()
     prof = {}
-    for cls, name in ((0, "msm_accumulate"), (1, "msm_total"), (2, "ntt")):
+    for cls, name in ((0, "msm_accumulate"), (1, "msm_total"), (2, "ntt"), (4, "msm_recode"), (5, "msm_tail"), (6, "quotient_eval")):
         ms, cnt = C.c_double(0), C.c_uint64(0)
         nat.check(L.b200_profile_read(cls, C.byref(ms), C.byref(cnt)))
         prof[name] = (ms.value, cnt.value)
@@ -632,6 +632,7 @@ def run_b200(args):
         "msm_pairs_per_s": round(pairs / world / (msm_ms * 1e-3), 1) * world if msm_ms > 0 else None,
         "ntt_elts_per_s": round(ntt_elts / world / (ntt_ms * 1e-3), 1) * world if ntt_ms > 0 else None,
         "msm_ms_per_step": round(msm_ms, 3), "ntt_ms_per_step": round(ntt_ms, 3),
+        "kernel_class_ms_per_step": {name: round(v[0] / args.steps, 3) for name, v in prof.items()},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -96,7 +96,7 @@ struct Config {
 const Config& config();
 
 // Optional device-side timing of kernel classes with CUDA events on the launching stream (bench.py's roofline leg).
-enum ProfClass { PROF_MSM_ACCUMULATE = 0, PROF_MSM_TOTAL = 1, PROF_NTT = 2, PROF_POLY = 3, PROF_NCLASS = 4 };
+enum ProfClass { PROF_MSM_ACCUMULATE = 0, PROF_MSM_TOTAL = 1, PROF_NTT = 2, PROF_POLY = 3, PROF_MSM_RECODE = 4, PROF_MSM_TAIL = 5, PROF_QUOTIENT = 6, PROF_NCLASS = 7 };
 bool prof_enabled();
 void prof_mark(int cls, cudaStream_t st, bool begin);
 struct ProfScope {

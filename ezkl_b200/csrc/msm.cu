@@ -23,6 +23,7 @@ namespace b200 {
 static constexpr int HEAVY_CHUNKS = 32;     // buckets with more chunks than this are summed by a whole block
 static constexpr int REDUCE_M_MAX = 32;      // buckets per thread in k_reduce: 8 for small batches (latency), 32 for large (work)
 static constexpr int TREE_THREADS = 256;
+static constexpr size_t AFFINE_MIN_ENTRIES = (size_t)1 << 62;     // auto-selection threshold (entries = columns * n * windows); see DESIGN.md §4.2
 
 int msm_default_window(size_t n) {
     int k = 0;
@@ -32,7 +33,8 @@ int msm_default_window(size_t n) {
     if (c > 22) c = 22;
     return c;
 }
-int msm_launches_per_run() { return 11; }
+static thread_local int tl_last_launches = 11;
+int msm_launches_per_run() { return tl_last_launches; }        // of the calling thread's last msm_run
 
 // ---------------------------------------------------------------------------------------------------------
 // table precomputation
@@ -395,7 +397,9 @@ static uint32_t pick_cap(size_t total_entries) {
 size_t msm_workspace_per_column(const MsmTable& t, size_t n) {
     const size_t nb = (size_t)1 << (t.c - 1), ents = n * t.W;
     const size_t chunk_stride = nb + ents / 16 + 1;
-    return ents * 4 + chunk_stride * (12 + sizeof(G1Xyzz)) + nb * (sizeof(G1Xyzz) + 24) + 65536;
+    const Config& cfg = config();
+    const size_t affine = cfg.msm_affine == 0 ? 0 : msm_affine_workspace_bytes(1, ents, chunk_stride);        // the point lists of the batched-affine path
+    return ents * 4 + chunk_stride * (12 + sizeof(G1Xyzz)) + nb * (sizeof(G1Xyzz) + 24) + 65536 + (cfg.msm_affine == 1 ? affine : 0);
 }
 
 int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int batch, G1Xyzz* d_out, MsmWorkspace& ws, cudaStream_t st, size_t base_off) {
@@ -410,7 +414,8 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const size_t ent_stride = (size_t)n * W;
     B200_CHECK(ent_stride < ((size_t)1 << 32), -1, "msm: n*W too large");
     const Config& cfg = config();
-    const bool use_affine = cfg.msm_affine == 1;
+    // batched-affine accumulation pays a fixed latency per round (one inversion kernel): only large batches amortise it
+    const bool use_affine = cfg.msm_affine == 1 || (cfg.msm_affine < 0 && ent_stride * (size_t)batch >= AFFINE_MIN_ENTRIES);
     uint32_t cap = pick_cap(ent_stride * batch);
     if (use_affine && cap > 128) cap = 128;          // the affine tree runs ceil(log2(cap)) rounds: keep it at 7
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
@@ -449,6 +454,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
 
     ProfScope ps_total(PROF_MSM_TOTAL, st);
     B200_CUDA(cudaMemsetAsync(hist, 0, counts_words * 4, st));
+    if (prof_enabled()) prof_mark(PROF_MSM_RECODE, st, true);
     const unsigned dig_blocks = min(div_up(n, 256), 148u * 8u);
     dim3 gd(dig_blocks, batch);
     k_digits<false><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, (uint32_t)base_off, c, W, nb, hist, nullptr, nullptr, 0, nullptr);
@@ -458,6 +464,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     k_len_offsets<<<batch, 32, 0, st>>>(len_hist, len_offs, cap);
     const unsigned ch_blocks = min(div_up(chunk_stride, 256), 148u * 8u);
     k_order_chunks<<<dim3(ch_blocks, batch), 256, 0, st>>>(chunk_len, chunk_stride, chunk_offs, nb, len_offs, len_cursor, cap, order);
+    if (prof_enabled()) prof_mark(PROF_MSM_RECODE, st, false);
     const unsigned acc_blocks = min(div_up(chunk_stride, 128), 148u * 16u);
     if (use_affine) {
         ProfScope ps(PROF_MSM_ACCUMULATE, st);
@@ -466,12 +473,14 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
         ProfScope ps(PROF_MSM_ACCUMULATE, st);
         k_accumulate<<<dim3(acc_blocks, batch), 128, 0, st>>>(t.d_table, ents, ent_stride, chunk_start, chunk_len, order, chunk_stride, chunk_offs, nb, chunk_sums);
     }
+    ProfScope ps_tail(PROF_MSM_TAIL, st);
     k_combine<<<dim3(div_up(nb, 128), batch), 128, 0, st>>>(chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     k_combine_heavy<<<dim3(32, batch), TREE_THREADS, 0, st>>>(heavy, heavy_stride, chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     if (cfg.msm_reduce2) k_reduce<2><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
     else k_reduce<1><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
     k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
     B200_CUDA(cudaGetLastError());
+    tl_last_launches = 10 + (use_affine ? msm_affine_launches(cap) : 1);
     return 0;
 }
 

@@ -1,18 +1,28 @@
 // msm_affine.cuh — batched-affine bucket accumulation (alternative to k_accumulate's XYZZ chain), host + device bodies.
 //
 // A chunk of L points of one bucket is summed as a binary tree: round r pairs up neighbours (2j, 2j+1) of the chunk's current
-// point list and writes the sums back, halving the list.  Affine addition needs one inversion per pair; all pairs of a round,
-// across every chunk of every column of the batch, share ONE level of Fermat inversions through Montgomery's trick applied
-// hierarchically: per thread (its chunk's pairs) -> groups of 32 threads -> groups of 32 groups -> a few thousand values that
-// are inverted in parallel.  Cost per pair: 1 multiply to accumulate the denominator product (phase A), 2 to peel its inverse
-// and 3 for lambda / x3 / y3 (phase C) = 6 + ~0.2 amortised, against 10.4 for the XYZZ mixed addition.
-// Phase A parks the running prefix product of pair j in the (still unused) output slot of pair j, so no extra scratch is needed.
-// Every per-thread body is a plain __host__ __device__ function of the global thread index, so the whole pipeline is also
-// runnable on the CPU (tests/test_host_logic.py) — the kernels in msm_affine.cu are loops-free wrappers around them.
+// point list and writes the sums back, halving the list.  An affine addition costs one inversion; all pairs of a round, across
+// every chunk of every column of the batch, share ONE level of inversions through Montgomery's trick:
+//   * a thread owns AFF_CPT chunks and treats all their pairs as one sequence: the producer side multiplies the pair denominators
+//     into a running product and parks the product-so-far of every pair; the consumer side starts from the inverse of the
+//     thread's total and peels the pairs in REVERSE order (inv_j = run * parked_j; run *= d_j);
+//   * the threads of a warp combine their totals with two shuffle scans (each lane gets the product of the OTHER 31 lanes and the
+//     warp total), so only one value per warp — a few thousand per round — needs a real (Fermat) inversion, done by one small
+//     kernel between rounds;
+//   * FUSION: the consumer of round r is also the producer of round r + 1 — as soon as two neighbouring sums exist it forms
+//     their denominator — so every point crosses HBM once per round (the round-1 version read the lists twice per round and
+//     launched seven kernels per round; this one launches two).  Because peeling reverses the order of accumulation, the
+//     direction alternates: the first producer pass runs ascending, round 0 descending, round 1 ascending, ...
+// Parked products live in the unused tail of the chunk's region of the list buffers, so the scratch is the two ping-pong point
+// lists plus 32 B per thread.  Cost per addition: 1 (parked product) + 2 (peel) + 3 (lambda, x3, y3; one is a squaring) = 5.8
+// multiply-equivalents + 12 per thread and round for the warp scans, against 9.46 for the XYZZ mixed addition.
+// Every per-thread body is a plain __host__ __device__ function, so the pipeline also runs on the CPU (tests/test_host_logic.py).
 #pragma once
 #include "ec.cuh"
 
 namespace b200 {
+
+static constexpr uint32_t AFF_CPT = 8;          // chunks per thread
 
 struct AffineArgs {
     const G1Affine* table;          // precomputed window table (round 0 input), indexed by entry & 0x7fffffff
@@ -21,18 +31,23 @@ struct AffineArgs {
     const uint32_t* chunk_len;
     const uint32_t* order;
     const uint32_t* chunk_offs;     // [col][nbuckets + 1]; last element = number of chunks of the column
-    G1Affine* pb_in;                // [col][ent_stride]  point list of the previous round (unused in round 0)
-    G1Affine* pb_out;               // [col][ent_stride]  point list this round writes (slot start + j)
-    Fq* thread_prod;                // [total_threads]    product of a thread's denominators (1 if idle)
-    Fq* thread_inv;                 // [total_threads]    its inverse (filled by the down sweep)
+    G1Affine* pb[2];                // ping-pong point lists [col][ent_stride]; round r reads pb[(r + 1) & 1] (r > 0), writes pb[r & 1]
+    Fq* thr_aux;                    // [threads] product of the other lanes' totals in the thread's warp (producer -> next consumer)
+    Fq* warp_prod;                  // [threads / 32] warp totals; inverted in place between the producer and the consumer
     uint64_t ent_stride, chunk_stride;
-    uint32_t nbuckets, round, batch;
+    uint32_t nbuckets, batch, threads_per_col, round, last_round;
 };
 
-// current list length of a chunk of `len` points before round r
+// list length of a chunk of `len` points before round r
 HD uint32_t aff_len_at(uint32_t len, uint32_t r) {
     for (uint32_t i = 0; i < r; ++i) len = (len + 1u) >> 1;
     return len;
+}
+// number of rounds a chunk of `len` points takes
+HD uint32_t aff_rounds_of(uint32_t len) {
+    uint32_t r = 0;
+    while (len > 1) { len = (len + 1u) >> 1; ++r; }
+    return r;
 }
 
 HD G1Affine aff_table_point(const AffineArgs& a, uint64_t col, uint32_t idx) {
@@ -42,7 +57,15 @@ HD G1Affine aff_table_point(const AffineArgs& a, uint64_t col, uint32_t idx) {
     return p;
 }
 HD G1Affine aff_input(const AffineArgs& a, uint64_t col, uint32_t start, uint32_t idx) {
-    return a.round == 0 ? aff_table_point(a, col, start + idx) : a.pb_in[col * a.ent_stride + start + idx];
+    return a.round == 0 ? aff_table_point(a, col, start + idx) : a.pb[(a.round + 1) & 1][col * a.ent_stride + start + idx];
+}
+// parked products of a chunk: the consumer of round r reads them behind the round's input list (round 0: at the chunk's start of
+// the otherwise unused buffer), the producer for round r + 1 writes them behind the round's output list
+HD Fq* aff_park_in(const AffineArgs& a, uint64_t col, uint32_t start, uint32_t len_r) {
+    return reinterpret_cast<Fq*>(a.pb[(a.round + 1) & 1] + col * a.ent_stride + start + (a.round == 0 ? 0u : len_r));
+}
+HD Fq* aff_park_out(const AffineArgs& a, uint64_t col, uint32_t start, uint32_t len_next) {
+    return reinterpret_cast<Fq*>(a.pb[a.round & 1] + col * a.ent_stride + start + len_next);
 }
 
 // Denominator of p + q: x_q - x_p in general, 2*y_p when p == q, and 1 whenever no inversion is needed
@@ -70,77 +93,83 @@ HD G1Affine aff_add_with_inv(const G1Affine& p, const G1Affine& q, const Fq& inv
     return o;
 }
 
-// thread -> (col, chunk); returns false when the thread has no pair to add in this round
-HD bool aff_thread_chunk(const AffineArgs& a, uint64_t g, uint64_t* col, uint32_t* start, uint32_t* len_r) {
-    *col = g / a.chunk_stride;
-    const uint32_t t = (uint32_t)(g % a.chunk_stride);
+// thread g -> (column, first chunk position); false when the thread lies outside the batch
+HD bool aff_thread(const AffineArgs& a, uint64_t g, uint64_t* col, uint32_t* pos0, uint32_t* nchunks) {
+    *col = g / a.threads_per_col;
     if (*col >= a.batch) return false;
-    const uint32_t nchunks = a.chunk_offs[*col * (a.nbuckets + 1) + a.nbuckets];
-    if (t >= nchunks) return false;
-    const uint32_t ch = a.order[*col * a.chunk_stride + t];
-    *start = a.chunk_start[*col * a.chunk_stride + ch];
-    *len_r = aff_len_at(a.chunk_len[*col * a.chunk_stride + ch], a.round);
-    return true;
+    *pos0 = (uint32_t)(g % a.threads_per_col) * AFF_CPT;
+    *nchunks = a.chunk_offs[*col * (a.nbuckets + 1) + a.nbuckets];
+    return *pos0 < *nchunks;
 }
 
-// x coordinate (and only it) of an input point: half the bytes of the point, which is all phase A needs in the general case
-HD Fq aff_input_x(const AffineArgs& a, uint64_t col, uint32_t start, uint32_t idx) {
-    if (a.round == 0) return a.table[a.ents[col * a.ent_stride + start + idx] & 0x7fffffffu].x;
-    return a.pb_in[col * a.ent_stride + start + idx].x;
-}
-// Phase A: denominators of the thread's pairs; prefix product of pair j parked in pb_out[start + j].x.
-// Only the x coordinates are read unless they coincide (identity operand, doubling or inverse pair), which needs the y's too.
-HD void aff_phase_a(const AffineArgs& a, uint64_t g) {
-    uint64_t col; uint32_t start, L;
+// First producer pass (before round 0), ascending: parks the running product of every pair's denominator, returns the thread's total.
+// Only the x coordinates are read unless they coincide or vanish (identity operand, doubling, inverse pair).
+HD Fq aff_first_pass(const AffineArgs& a, uint64_t g) {
+    uint64_t col; uint32_t pos0, nchunks;
     Fq acc = fp_one<FqTag>();
-    if (aff_thread_chunk(a, g, &col, &start, &L) && L >= 2) {
-        const uint32_t K = L >> 1;
-        for (uint32_t j = 0; j < K; ++j) {
-            const Fq px = aff_input_x(a, col, start, 2 * j), qx = aff_input_x(a, col, start, 2 * j + 1);
-            a.pb_out[col * a.ent_stride + start + j].x = acc;
+    if (!aff_thread(a, g, &col, &pos0, &nchunks)) return acc;
+    for (uint32_t c = 0; c < AFF_CPT && pos0 + c < nchunks; ++c) {
+        const uint32_t ch = a.order[col * a.chunk_stride + pos0 + c];
+        const uint32_t start = a.chunk_start[col * a.chunk_stride + ch], L = a.chunk_len[col * a.chunk_stride + ch];
+        Fq* park = aff_park_in(a, col, start, L);
+        for (uint32_t j = 0; j < (L >> 1); ++j) {
+            const uint32_t e0 = a.ents[col * a.ent_stride + start + 2 * j], e1 = a.ents[col * a.ent_stride + start + 2 * j + 1];
+            const Fq px = a.table[e0 & 0x7fffffffu].x, qx = a.table[e1 & 0x7fffffffu].x;
             Fq d = qx - px;
-            if (fp_is_zero(d) || fp_is_zero(px) || fp_is_zero(qx))       // rare: fall back to the complete rule (needs y)
-                d = aff_denominator(aff_input(a, col, start, 2 * j), aff_input(a, col, start, 2 * j + 1));
+            if (fp_is_zero(d) || fp_is_zero(px) || fp_is_zero(qx)) d = aff_denominator(aff_table_point(a, col, start + 2 * j), aff_table_point(a, col, start + 2 * j + 1));
+            park[j] = acc;
             acc = acc * d;
         }
     }
-    a.thread_prod[g] = acc;
-}
-// Phase C: peel the inverses off from the last pair to the first, finish the additions, carry an odd leftover over
-HD void aff_phase_c(const AffineArgs& a, uint64_t g) {
-    uint64_t col; uint32_t start, L;
-    if (!aff_thread_chunk(a, g, &col, &start, &L) || L < 2) {
-        // chunks that are already down to one point still have to appear in this round's output list
-        if (aff_thread_chunk(a, g, &col, &start, &L) && L == 1) a.pb_out[col * a.ent_stride + start] = aff_input(a, col, start, 0);
-        return;
-    }
-    const uint32_t K = L >> 1;
-    G1Affine* out = a.pb_out + col * a.ent_stride + start;
-    G1Affine leftover;
-    const bool odd = (L & 1u) != 0;
-    if (odd) leftover = aff_input(a, col, start, L - 1);
-    Fq run = a.thread_inv[g];
-    for (uint32_t j = K; j-- > 0;) {
-        const G1Affine p = aff_input(a, col, start, 2 * j), q = aff_input(a, col, start, 2 * j + 1);
-        const Fq inv = run * out[j].x;               // prefix product of pairs < j was parked here by phase A
-        run = run * aff_denominator(p, q);
-        out[j] = aff_add_with_inv(p, q, inv);
-    }
-    if (odd) out[K] = leftover;
+    return acc;
 }
 
-// Hierarchy: products of groups of AFF_GROUP consecutive values with exclusive prefix products kept for the way down.
-static constexpr uint32_t AFF_GROUP = 32;
-HD void aff_up(const Fq* vals, uint64_t n_vals, Fq* prefix, Fq* group_prod, uint64_t u) {
-    const uint64_t lo = u * AFF_GROUP, hi = lo + AFF_GROUP < n_vals ? lo + AFF_GROUP : n_vals;
-    Fq acc = fp_one<FqTag>();
-    for (uint64_t i = lo; i < hi; ++i) { prefix[i] = acc; acc = acc * vals[i]; }
-    group_prod[u] = acc;
+// Round r: consumer of the round's pairs and producer for round r + 1.  `inv_total` = inverse of this thread's denominator total
+// for round r; returns the thread's total for round r + 1 (1 on the last round).
+HD Fq aff_round(const AffineArgs& a, uint64_t g, Fq inv_total) {
+    uint64_t col; uint32_t pos0, nchunks;
+    Fq acc2 = fp_one<FqTag>();
+    if (!aff_thread(a, g, &col, &pos0, &nchunks)) return acc2;
+    const bool desc = (a.round & 1u) == 0;
+    const bool produce = !a.last_round;
+    Fq run = inv_total;
+    uint32_t cnt = nchunks - pos0 < AFF_CPT ? nchunks - pos0 : AFF_CPT;
+    for (uint32_t cc = 0; cc < cnt; ++cc) {
+        const uint32_t c = desc ? cnt - 1 - cc : cc;
+        const uint32_t ch = a.order[col * a.chunk_stride + pos0 + c];
+        const uint32_t start = a.chunk_start[col * a.chunk_stride + ch];
+        const uint32_t L = aff_len_at(a.chunk_len[col * a.chunk_stride + ch], a.round);
+        if (L < 2) continue;                                    // finished chunks rest where they finished
+        const uint32_t K = L >> 1, odd = L & 1u, Ln = K + odd;
+        const Fq* park = aff_park_in(a, col, start, L);
+        Fq* park2 = aff_park_out(a, col, start, Ln);
+        G1Affine* out = a.pb[a.round & 1] + col * a.ent_stride + start;
+        G1Affine held; held.x = fp_zero<FqTag>(); held.y = fp_zero<FqTag>();
+        for (uint32_t ii = 0; ii < Ln; ++ii) {
+            const uint32_t i = desc ? Ln - 1 - ii : ii;
+            G1Affine e;
+            if (odd && i == K) e = aff_input(a, col, start, L - 1);           // the odd leftover passes through
+            else {
+                const G1Affine p = aff_input(a, col, start, 2 * i), q = aff_input(a, col, start, 2 * i + 1);
+                const Fq inv = run * park[i];
+                run = run * aff_denominator(p, q);
+                e = aff_add_with_inv(p, q, inv);
+            }
+            out[i] = e;
+            if (!produce) continue;
+            // next round pairs (2m, 2m+1) of the output list; an odd-length list leaves its last element unpaired
+            if ((i & 1u) == (desc ? 1u : 0u)) held = e;                       // first member of its pair in this direction
+            else if (!((Ln & 1u) && i == Ln - 1)) {
+                const Fq d2 = desc ? aff_denominator(e, held) : aff_denominator(held, e);
+                park2[i >> 1] = acc2;
+                acc2 = acc2 * d2;
+            }
+        }
+    }
+    return acc2;
 }
-HD void aff_down(const Fq* vals, uint64_t n_vals, const Fq* prefix, const Fq* group_inv, Fq* inv_out, uint64_t u) {
-    const uint64_t lo = u * AFF_GROUP, hi = lo + AFF_GROUP < n_vals ? lo + AFF_GROUP : n_vals;
-    Fq run = group_inv[u];
-    for (uint64_t i = hi; i-- > lo;) { const Fq v = vals[i]; inv_out[i] = run * prefix[i]; run = run * v; }
-}
+// In the descending direction the unpaired last element (index Ln - 1, even) arrives first and must not be taken for a pair
+// member: it is even, so `held` is not touched (desc holds odd indices) and the pairing branch is skipped by the explicit test.
+// In the ascending direction it arrives last, is even, and only overwrites `held`.
 
 }  // namespace b200

@@ -102,6 +102,7 @@ int quotient_eval_run(const Fr* const* h_col_ptrs, size_t n_cols, uint32_t ext_k
     const uint32_t blob_u4 = (uint32_t)((total + 15) / 16);
     const size_t smem = (size_t)blob_u4 * 16;
     const dim3 grid(div_up(N, 128));
+    ProfScope ps(PROF_QUOTIENT, st);
 #define B200_QLAUNCH(NS)                                                                                                              \
     do {                                                                                                                              \
         B200_CUDA(cudaFuncSetAttribute(k_quotient_eval<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 64));            \

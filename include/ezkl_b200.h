@@ -59,7 +59,8 @@ int b200_version(void);
 uint64_t b200_launch_count(void);
 
 /* device-side timing of kernel classes with CUDA events on the launching stream (off by default).
- * cls: 0 = MSM bucket-accumulation kernel, 1 = whole MSM pipeline, 2 = NTT (all passes of a call), 3 = poly.
+ * cls: 0 = MSM bucket-accumulation kernel, 1 = whole MSM pipeline, 2 = NTT (all passes of a call), 3 = poly, 4 = MSM digit recoding +
+ * bucket sort (kernels 1-6), 5 = MSM tail (combine, bucket reduction, final sum), 6 = evaluate_h kernel.
  * b200_profile_enable(1) clears earlier records; b200_profile_read synchronises the device and sums the class. */
 int b200_profile_enable(int on);
 int b200_profile_read(int cls, double* total_ms, uint64_t* count);

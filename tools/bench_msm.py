@@ -50,8 +50,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":          # one k=17, c=16, batch-60 call after a warm-up (for ncu launch lists)
         n = 1 << 17
         bases = dev.DeviceBases(dev.generate_bases(n, seed=3), window_bits=16)
-        sc = dev.random_scalars(n, batch=60, seed=5)
-        print("k=17 c=16 batch=60: %.3f ms" % run(bases, sc, reps=2))
+        batches = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [60]
+        for b in batches:
+            sc = dev.random_scalars(n, batch=b, seed=5)
+            ms = run(bases, sc, reps=3)
+            print("k=17 c=16 batch=%d: %.3f ms  (%.1f M pairs/s, accumulate path: B200_MSM_AFFINE=%s)" % (b, ms, b * n / ms / 1e3, os.environ.get("B200_MSM_AFFINE", "default")), flush=True)
+            del sc
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sweep":
         sweep()
