@@ -36,7 +36,6 @@ static void read_config() {
     c.ntt_nofull = getenv("B200_NTT_NOFULL") != nullptr;
     c.msm_reduce_m = env_int("B200_MSM_REDUCE_M", 0);
     c.msm_reduce2 = env_int("B200_MSM_REDUCE2", 0);
-    c.msm_affine = env_int("B200_MSM_AFFINE", -1);
     c.shard_min_logn = env_int("B200_SHARD_MIN_LOGN", 22);
     g_cfg = c;
 }
@@ -76,7 +75,7 @@ struct Ctx {
     bool has_last = false;
     void release() {
         cudaSetDevice(dev);
-        DevBuf* bufs[] = {&msm_ws.counts, &msm_ws.offs, &msm_ws.ents, &msm_ws.subs, &msm_ws.sums, &msm_ws.misc, &msm_ws.affine, &poly_ws.scratch, &quot_ws.prog,
+        DevBuf* bufs[] = {&msm_ws.counts, &msm_ws.offs, &msm_ws.ents, &msm_ws.subs, &msm_ws.sums, &msm_ws.misc, &poly_ws.scratch, &quot_ws.prog,
                           &stage_a, &stage_b, &stage_c, &small};
         for (DevBuf* b : bufs) b->release();
         ring.release(); poly_ws.ring.release(); quot_ws.ring.release();

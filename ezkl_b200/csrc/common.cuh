@@ -90,7 +90,6 @@ struct Config {
     int ntt_nofull = 0;             // B200_NTT_NOFULL: two-level inter-pass twiddles even when the full table exists
     int msm_reduce_m = 0;           // B200_MSM_REDUCE_M
     int msm_reduce2 = 0;            // B200_MSM_REDUCE2
-    int msm_affine = -1;            // B200_MSM_AFFINE: 1 forces the batched-affine accumulation, 0 the XYZZ chain, -1 picks by work size
     int shard_min_logn = 22;        // B200_SHARD_MIN_LOGN: a single transform of at least this size is sharded across the devices
 };
 const Config& config();

@@ -5,6 +5,7 @@
 #include <vector>
 #include "msm.cuh"
 #include "../../tools/experiments/fd.cuh"
+#include "../../tools/experiments/msm_affine.cuh"
 
 namespace b200 {
 template <class Tag>

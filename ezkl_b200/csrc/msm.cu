@@ -23,7 +23,6 @@ namespace b200 {
 static constexpr int HEAVY_CHUNKS = 32;     // buckets with more chunks than this are summed by a whole block
 static constexpr int REDUCE_M_MAX = 32;      // buckets per thread in k_reduce: 8 for small batches (latency), 32 for large (work)
 static constexpr int TREE_THREADS = 256;
-static constexpr size_t AFFINE_MIN_ENTRIES = (size_t)1 << 62;     // auto-selection threshold (entries = columns * n * windows); see DESIGN.md §4.2
 
 int msm_default_window(size_t n) {
     int k = 0;
@@ -33,8 +32,7 @@ int msm_default_window(size_t n) {
     if (c > 22) c = 22;
     return c;
 }
-static thread_local int tl_last_launches = 11;
-int msm_launches_per_run() { return tl_last_launches; }        // of the calling thread's last msm_run
+int msm_launches_per_run() { return 11; }
 
 // ---------------------------------------------------------------------------------------------------------
 // table precomputation
@@ -397,9 +395,7 @@ static uint32_t pick_cap(size_t total_entries) {
 size_t msm_workspace_per_column(const MsmTable& t, size_t n) {
     const size_t nb = (size_t)1 << (t.c - 1), ents = n * t.W;
     const size_t chunk_stride = nb + ents / 16 + 1;
-    const Config& cfg = config();
-    const size_t affine = cfg.msm_affine == 0 ? 0 : msm_affine_workspace_bytes(1, ents, chunk_stride);        // the point lists of the batched-affine path
-    return ents * 4 + chunk_stride * (12 + sizeof(G1Xyzz)) + nb * (sizeof(G1Xyzz) + 24) + 65536 + (cfg.msm_affine == 1 ? affine : 0);
+    return ents * 4 + chunk_stride * (12 + sizeof(G1Xyzz)) + nb * (sizeof(G1Xyzz) + 24) + 65536;
 }
 
 int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int batch, G1Xyzz* d_out, MsmWorkspace& ws, cudaStream_t st, size_t base_off) {
@@ -414,10 +410,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const size_t ent_stride = (size_t)n * W;
     B200_CHECK(ent_stride < ((size_t)1 << 32), -1, "msm: n*W too large");
     const Config& cfg = config();
-    // batched-affine accumulation pays a fixed latency per round (one inversion kernel): only large batches amortise it
-    const bool use_affine = cfg.msm_affine == 1 || (cfg.msm_affine < 0 && ent_stride * (size_t)batch >= AFFINE_MIN_ENTRIES);
-    uint32_t cap = pick_cap(ent_stride * batch);
-    if (use_affine && cap > 128) cap = 128;          // the affine tree runs ceil(log2(cap)) rounds: keep it at 7
+    const uint32_t cap = pick_cap(ent_stride * batch);
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
     uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
@@ -466,10 +459,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     k_order_chunks<<<dim3(ch_blocks, batch), 256, 0, st>>>(chunk_len, chunk_stride, chunk_offs, nb, len_offs, len_cursor, cap, order);
     if (prof_enabled()) prof_mark(PROF_MSM_RECODE, st, false);
     const unsigned acc_blocks = min(div_up(chunk_stride, 128), 148u * 16u);
-    if (use_affine) {
-        ProfScope ps(PROF_MSM_ACCUMULATE, st);
-        if (int rc = msm_accumulate_affine(t, ents, ent_stride, chunk_start, chunk_len, order, chunk_stride, chunk_offs, nb, cap, batch, chunk_sums, ws.affine, st)) return rc;
-    } else {
+    {
         ProfScope ps(PROF_MSM_ACCUMULATE, st);
         k_accumulate<<<dim3(acc_blocks, batch), 128, 0, st>>>(t.d_table, ents, ent_stride, chunk_start, chunk_len, order, chunk_stride, chunk_offs, nb, chunk_sums);
     }
@@ -480,7 +470,6 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     else k_reduce<1><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
     k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
     B200_CUDA(cudaGetLastError());
-    tl_last_launches = 10 + (use_affine ? msm_affine_launches(cap) : 1);
     return 0;
 }
 

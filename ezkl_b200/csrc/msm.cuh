@@ -17,18 +17,10 @@ struct MsmTable {
 };
 
 struct MsmWorkspace {
-    DevBuf counts, offs, ents, subs, sums, misc, affine;
+    DevBuf counts, offs, ents, subs, sums, misc;
 };
 
 int msm_default_window(size_t n);
-// batched-affine alternative to the XYZZ accumulation kernel (msm_affine.cu)
-size_t msm_affine_workspace_bytes(size_t batch, size_t ent_stride, size_t chunk_stride);
-int msm_accumulate_affine(const MsmTable& t, const uint32_t* ents, size_t ent_stride, const uint32_t* chunk_start, const uint32_t* chunk_len,
-                          const uint32_t* order, size_t chunk_stride, const uint32_t* chunk_offs, uint32_t nbuckets, uint32_t cap, int batch,
-                          G1Xyzz* chunk_sums, DevBuf& scratch, cudaStream_t st);
-int msm_affine_launches(uint32_t cap);
-int msm_affine_host_chunks(const G1Affine* table, const uint32_t* ents, size_t n_ents, const uint32_t* chunk_start, const uint32_t* chunk_len,
-                           size_t nchunks, G1Affine* out);
 // Builds the table from n affine points already on the device (copied; caller keeps ownership of d_bases).
 int msm_table_build(MsmTable* t, const G1Affine* d_bases, size_t n, int c, cudaStream_t st);
 void msm_table_free(MsmTable* t);

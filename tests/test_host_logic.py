@@ -171,7 +171,7 @@ def test_fp64_pipe_multiplier_vs_bigint():
 
 
 def test_batched_affine_accumulation_bodies_on_host():
-    """msm_affine.cuh run on the CPU: every chunk's tree of batched-affine additions (hierarchical Montgomery trick) must equal
+    """tools/experiments/msm_affine.cuh (the batched-affine accumulation EXPERIMENT, not in the product library) run on the CPU: every chunk's tree of batched-affine additions (hierarchical Montgomery trick) must equal
     the plain sum of its points — incl. repeated points (doubling), P + (-P), identity entries, negated entries, length-1 chunks."""
     L = nat.lib()
     rng = random.Random(8)

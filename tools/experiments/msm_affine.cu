@@ -1,8 +1,9 @@
-// msm_affine.cu — kernels and orchestration of the fused batched-affine bucket accumulation (see msm_affine.cuh).
-// Per MSM call: one producer pass, then per round one fused consumer/producer kernel and one small inversion kernel, then the
-// hand-over to the XYZZ combine / reduce tail.  msm.cu picks this path for large batches (config().msm_affine: 1 always, 0 never).
+// msm_affine.cu — EXPERIMENT, not part of libezkl_b200.so: kernels and orchestration of the fused batched-affine bucket accumulation
+// (see msm_affine.cuh).  Per MSM call: one producer pass, then per round one fused consumer/producer kernel and one small inversion
+// kernel, then the hand-over to the XYZZ combine / reduce tail.  Wired into msm_run at commit e30e8c9 it is bit-exact and 2.1x slower
+// than the XYZZ chain (profiles/r02_msm_affine_fused_vs_xyzz.txt); the host bodies stay under test through the debug library.
 #include <vector>
-#include "msm.cuh"
+#include "../../ezkl_b200/csrc/msm.cuh"
 #include "msm_affine.cuh"
 
 namespace b200 {
@@ -115,7 +116,7 @@ int msm_accumulate_affine(const MsmTable& t, const uint32_t* ents, size_t ent_st
     B200_CUDA(cudaGetLastError());
     return 0;
 }
-int msm_affine_launches(uint32_t cap) {
+int msm_affine_launches(uint32_t cap) {      // kernels msm_accumulate_affine launches
     uint32_t rounds = 0;
     while ((1u << rounds) < cap) ++rounds;
     return (int)(2 * rounds + 2);

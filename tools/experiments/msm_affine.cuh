@@ -1,4 +1,5 @@
-// msm_affine.cuh — batched-affine bucket accumulation (alternative to k_accumulate's XYZZ chain), host + device bodies.
+// msm_affine.cuh — EXPERIMENT (not in the product library): batched-affine bucket accumulation, an alternative to k_accumulate's
+// XYZZ chain; host + device bodies.
 //
 // A chunk of L points of one bucket is summed as a binary tree: round r pairs up neighbours (2j, 2j+1) of the chunk's current
 // point list and writes the sums back, halving the list.  An affine addition costs one inversion; all pairs of a round, across
@@ -18,9 +19,19 @@
 // multiply-equivalents + 12 per thread and round for the warp scans, against 9.46 for the XYZZ mixed addition.
 // Every per-thread body is a plain __host__ __device__ function, so the pipeline also runs on the CPU (tests/test_host_logic.py).
 #pragma once
-#include "ec.cuh"
+#include "../../ezkl_b200/csrc/ec.cuh"
 
 namespace b200 {
+
+struct MsmTable;
+struct DevBuf;
+size_t msm_affine_workspace_bytes(size_t batch, size_t ent_stride, size_t chunk_stride);
+int msm_accumulate_affine(const MsmTable& t, const uint32_t* ents, size_t ent_stride, const uint32_t* chunk_start, const uint32_t* chunk_len,
+                          const uint32_t* order, size_t chunk_stride, const uint32_t* chunk_offs, uint32_t nbuckets, uint32_t cap, int batch,
+                          G1Xyzz* chunk_sums, DevBuf& scratch, cudaStream_t st);
+int msm_affine_launches(uint32_t cap);
+int msm_affine_host_chunks(const G1Affine* table, const uint32_t* ents, size_t n_ents, const uint32_t* chunk_start, const uint32_t* chunk_len,
+                           size_t nchunks, G1Affine* out);
 
 static constexpr uint32_t AFF_CPT = 8;          // chunks per thread
 
