@@ -450,14 +450,13 @@ def run_b200(args):
                 hq = np.zeros((N_ext, 4), np.uint64)
                 for g0 in range(0, ncoset, group):
                     m = min(group, ncoset - g0)
-                    exts = dom.coeff_to_extended_batch([coeffs[(g0 + j) % len(coeffs)] for j in range(m)])
-                    h2d += m * n * 32; d2h += m * N_ext * 32
+                    last = g0 + group >= ncoset
                     prog = programs.setdefault(m, gate_program(m))
-                    hq = ev.evaluate_h(prog, exts + [hq], k, ext_k)
-                    h2d += (m + 1) * N_ext * 32; d2h += N_ext * 32
-                hq = dom.divide_by_vanishing_poly(hq)
-                hp["h"] = dom.extended_to_coeff(hq)
-                h2d += 2 * N_ext * 32; d2h += 2 * N_ext * 32
+                    # b200_evaluate_h: coefficient columns in (n each), the running sum as an extended column; the last group also divides by
+                    # the vanishing polynomial and returns the quotient's coefficients
+                    hq = ev.evaluate_h_from_polys(prog, [coeffs[(g0 + j) % len(coeffs)] for j in range(m)] + [hq], dom, finish=last)
+                    h2d += m * n * 32 + N_ext * 32; d2h += N_ext * 32
+                hp["h"] = hq[: tr["quotient_pieces"] * n]
             elif kind == "eval":
                 done = 0
                 while done < count:
@@ -550,8 +549,8 @@ def run_b200(args):
         for _ in range(hp_steps):
             hp_h2d, hp_d2h = step_host_pointer()
         e2e_hp = {"value": round((time.perf_counter() - t0) / hp_steps, 6), "unit": "s", "h2d_bytes_per_step": int(hp_h2d), "d2h_bytes_per_step": int(hp_d2h), "steps": hp_steps,
-                  "how": "host-pointer entry points only (b200_msm_batch, b200_ifft_batch, b200_coeff_to_extended_batch, b200_quotient_eval, ...) on pageable numpy "
-                         "buffers; every operand and result crosses PCIe on every call (INTEGRATION.md §2a)"}
+                  "how": "host-pointer entry points only (b200_msm_batch, b200_ifft_batch, b200_evaluate_h on coefficient columns, b200_poly_eval_batch, ...) on "
+                         "pageable numpy buffers; every operand and result crosses PCIe on every call (INTEGRATION.md §2a)"}
     # ---- N > 1: ONE process (rank 0) owning all N devices through b200_init_multi, same host-pointer trace; the library deals
     #      columns / splits bases / shards transforms itself (device workers).  The other ranks idle on the rendezvous store.
     in_process = None

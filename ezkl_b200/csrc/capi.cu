@@ -1118,5 +1118,74 @@ int b200_quotient_eval(const b200_fr* const* columns, size_t n_columns, uint32_t
     return 0;
 }
 
+// evaluate_h at its natural boundary: the CPU evaluator receives coefficient-form polynomials and builds their cosets itself
+// (UPSTREAM plonk/evaluation.rs: `advice_polys.iter().map(|a| domain.coeff_to_extended(a))`), and vanishing/prover.rs then divides by
+// the vanishing polynomial and converts back.  One call does the same on the device, so a coefficient column crosses PCIe once
+// (n elements) instead of its coset twice (2^ext_k down, 2^ext_k up).
+int b200_evaluate_h(const b200_fr* const* polys, const size_t* lengths, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_fr* ext_omega, const b200_fr* zeta,
+                    const b200_col_ref* loads, size_t n_loads, const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr,
+                    const b200_fr* t_evaluations, uint32_t t_period, const b200_fr* ext_omega_inv, const b200_fr* ext_ifft_divisor, b200_fr* out) {
+    B200_ENTER(c, nullptr);
+    B200_CHECK(out && ext_omega && zeta && (n_columns == 0 || (polys && lengths)), -1, "evaluate_h: null pointer");
+    B200_CHECK(ext_k >= k && ext_k >= 1 && ext_k <= 28, -1, "evaluate_h: need k <= ext_k <= 28");
+    B200_CHECK(!t_evaluations || (t_period >= 1 && t_period <= 1024 && ext_omega_inv && ext_ifft_divisor), -1, "evaluate_h: finishing needs t_evaluations, its period and the inverse-transform constants");
+    const size_t N = (size_t)1 << ext_k;
+    size_t n_coeff_cols = 0, max_len = 0;
+    for (size_t i = 0; i < n_columns; ++i) {
+        B200_CHECK(polys[i] && lengths[i] >= 1 && lengths[i] <= N, -1, "evaluate_h: column %zu is null or longer than 2^ext_k", i);
+        if (lengths[i] < N) { ++n_coeff_cols; if (lengths[i] > max_len) max_len = lengths[i]; }
+    }
+    // device layout: stage_c = every column on the extended domain, stage_a = coefficient staging (one sub-batch), stage_b = NTT scratch / output
+    if (c->stage_c.ensure(sizeof(Fr) * N * (n_columns ? n_columns : 1))) return -2;
+    size_t sub = n_coeff_cols ? call_budget() / (sizeof(Fr) * (N + max_len)) : 1;
+    if (sub < 1) sub = 1;
+    if (sub > n_coeff_cols) sub = n_coeff_cols ? n_coeff_cols : 1;
+    if (c->stage_a.ensure(sizeof(Fr) * (max_len ? max_len : 1) * sub) || c->stage_b.ensure(sizeof(Fr) * N * sub)) return -2;
+    StreamScope ss(c, nullptr);
+    Fr* ext = c->stage_c.as<Fr>();
+    NttScale pre, none;
+    pre.mode = 3; pre.c[0] = fp_one<FrTag>(); pre.c[1] = as_fr(zeta); pre.c[2] = as_fr(zeta) * as_fr(zeta);
+    std::vector<size_t> group;           // coefficient columns of equal length are transformed together
+    auto flush = [&](size_t len) -> int {
+        if (group.empty()) return 0;
+        for (size_t p = 0; p < group.size(); ++p)
+            B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + p * len, polys[group[p]], sizeof(Fr) * len, cudaMemcpyHostToDevice, ss.st));
+        // transform into scratch-free destinations: each polynomial lands in its own column of `ext` (dst stride = distance between them is
+        // irregular, so one launch per run of consecutive column indices)
+        size_t p0 = 0;
+        while (p0 < group.size()) {
+            size_t p1 = p0 + 1;
+            while (p1 < group.size() && group[p1] == group[p1 - 1] + 1) ++p1;
+            if (int rc = ntt_call(c, c->stage_a.as<Fr>() + p0 * len, len, len, c->stage_b.as<Fr>(), ext + group[p0] * N, N, ext_k, as_fr(ext_omega), pre, none, (int)(p1 - p0), ss.st)) return rc;
+            p0 = p1;
+        }
+        B200_CUDA(cudaStreamSynchronize(ss.st));          // the coefficient staging buffer is reused by the next group
+        group.clear();
+        return 0;
+    };
+    size_t cur_len = 0;
+    for (size_t i = 0; i < n_columns; ++i) {
+        if (lengths[i] == N) { B200_CUDA(cudaMemcpyAsync(ext + i * N, polys[i], sizeof(Fr) * N, cudaMemcpyHostToDevice, ss.st)); continue; }
+        if (!group.empty() && (lengths[i] != cur_len || group.size() == sub)) { if (int rc = flush(cur_len)) return rc; }
+        cur_len = lengths[i];
+        group.push_back(i);
+    }
+    if (int rc = flush(cur_len)) return rc;
+    std::vector<const void*> ptrs(n_columns);
+    for (size_t i = 0; i < n_columns; ++i) ptrs[i] = ext + i * N;
+    Fr* h = c->stage_b.as<Fr>();
+    if (int rc = b200_quotient_eval_dev(ptrs.data(), n_columns, k, ext_k, loads, n_loads, constants, n_constants, program, n_instr, h, ss.st)) return rc;
+    if (t_evaluations) {
+        if (int rc = b200_poly_scale_cycle_dev(h, N, t_evaluations, t_period, ss.st)) return rc;
+        NttScale post;
+        const Fr z = as_fr(zeta), z2 = z * z, d = as_fr(ext_ifft_divisor);
+        post.mode = 3; post.c[0] = d; post.c[1] = d * z2; post.c[2] = d * z;
+        if (int rc = ntt_call(c, h, N, N, ext, h, N, ext_k, as_fr(ext_omega_inv), none, post, 1, ss.st)) return rc;      // `ext` is free again: scratch
+    }
+    B200_CUDA(cudaMemcpyAsync(out, h, sizeof(Fr) * N, cudaMemcpyDeviceToHost, ss.st));
+    B200_CUDA(cudaStreamSynchronize(ss.st));
+    return 0;
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

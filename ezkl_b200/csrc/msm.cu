@@ -17,6 +17,7 @@
 // HBM traffic per (scalar, base) pair: 32 B scalar (read twice) + W x 64 B table gathers; the kernel is bound by
 // integer issue (IMAD.WIDE), not HBM — see DESIGN.md §kernels.
 #include "msm.cuh"
+#include "ec_coop.cuh"
 
 namespace b200 {
 
@@ -326,6 +327,48 @@ __global__ void __launch_bounds__(TREE_THREADS) k_final(const G1Xyzz* __restrict
     if (threadIdx.x == 0) out[col] = acc;
 }
 
+// ---- four-lane cooperative variants of 10 / 11 (ec_coop.cuh): a quad of lanes is one logical thread, a CTA holds COOP_LT of them ----
+static constexpr int COOP_LT = TREE_THREADS / 4;
+DEV G1Xyzz block_sum_coop(G1Xyzz v, G1Xyzz* sh) {
+    const unsigned lt = threadIdx.x >> 2, q = threadIdx.x & 3;
+    if (q == 0) sh[lt] = v;
+    __syncthreads();
+#pragma unroll 1
+    for (unsigned s = COOP_LT / 2; s > 0; s >>= 1) {
+        if (lt < s) { v = g1_add_coop4(v, sh[lt + s]); if (q == 0) sh[lt] = v; }
+        __syncthreads();
+    }
+    return v;
+}
+__global__ void __launch_bounds__(TREE_THREADS) k_reduce_coop(const G1Xyzz* __restrict__ bucket_sums, uint32_t nbuckets, G1Xyzz* __restrict__ partials, uint32_t nparts, uint32_t per_thread) {
+    __shared__ G1Xyzz sh[COOP_LT];
+    const uint32_t col = blockIdx.y;
+    const G1Xyzz* bs = bucket_sums + (size_t)col * nbuckets;
+    const uint32_t t = blockIdx.x * COOP_LT + (threadIdx.x >> 2);
+    const uint32_t lo = t * per_thread;
+    G1Xyzz run = g1_xyzz_identity(), acc = g1_xyzz_identity();
+    if (lo < nbuckets) {
+        const uint32_t hi = min(lo + per_thread, nbuckets);
+#pragma unroll 1
+        for (uint32_t b = hi; b-- > lo;) {
+            run = g1_add_coop4(run, bs[b]);
+            acc = g1_add_coop4(acc, run);
+        }
+        if (lo > 0) acc = g1_add_coop4(acc, g1_mul_small_coop4(run, lo));
+    }
+    acc = block_sum_coop(acc, sh);
+    if (threadIdx.x == 0) partials[(size_t)col * nparts + blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(TREE_THREADS) k_final_coop(const G1Xyzz* __restrict__ partials, uint32_t nparts, G1Xyzz* __restrict__ out) {
+    __shared__ G1Xyzz sh[COOP_LT];
+    const uint32_t col = blockIdx.x;
+    G1Xyzz acc = g1_xyzz_identity();
+#pragma unroll 1
+    for (uint32_t j = threadIdx.x >> 2; j < nparts; j += COOP_LT) acc = g1_add_coop4(acc, partials[(size_t)col * nparts + j]);
+    acc = block_sum_coop(acc, sh);
+    if (threadIdx.x == 0) out[col] = acc;
+}
+
 // synthetic distinct bases for benchmarks / tests: out[i] = [h(seed, i)] * G, affine (G = (1, 2))
 __global__ void __launch_bounds__(128) k_g1_generate(uint64_t seed, size_t n, G1Affine* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,7 +421,7 @@ int g1_fixed_base_mul_run(const Fr* d_scalars, size_t n, const G1Affine& base, G
 int g1_sum_run(const G1Xyzz* d_points, size_t groups, size_t count, G1Xyzz* d_out, cudaStream_t st) {
     if (groups == 0) return 0;
     B200_CHECK(groups <= 0x7fffffffu && count <= 0xffffffffu, -1, "g1_sum: sizes out of range");
-    k_final<<<(unsigned)groups, TREE_THREADS, 0, st>>>(d_points, (uint32_t)count, d_out);
+    k_final_coop<<<(unsigned)groups, TREE_THREADS, 0, st>>>(d_points, (uint32_t)count, d_out);
     B200_CUDA(cudaGetLastError());
     return 0;
 }
@@ -415,7 +458,9 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
     uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
     if (cfg.msm_reduce_m >= 1 && cfg.msm_reduce_m <= 4096) reduce_m = (uint32_t)cfg.msm_reduce_m;    // tuning override
-    const uint32_t nparts = div_up(div_up(nb, reduce_m), TREE_THREADS);
+    const bool coop = cfg.msm_reduce2 == 0;               // B200_MSM_REDUCE2=1 falls back to the one-lane-per-thread tail
+    if (coop && reduce_m > 8) reduce_m = 16;             // four lanes per logical thread: 4x the warps for the same buckets per thread
+    const uint32_t nparts = div_up(div_up(nb, reduce_m), coop ? COOP_LT : TREE_THREADS);
 
     // counts region (zeroed every call): hist | cursor | len_hist | len_cursor | heavy
     const size_t n_hist = (size_t)batch * nb, n_len = (size_t)batch * (cap + 1), n_heavy = (size_t)batch * heavy_stride;
@@ -466,9 +511,13 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     ProfScope ps_tail(PROF_MSM_TAIL, st);
     k_combine<<<dim3(div_up(nb, 128), batch), 128, 0, st>>>(chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
     k_combine_heavy<<<dim3(32, batch), TREE_THREADS, 0, st>>>(heavy, heavy_stride, chunk_offs, nb, chunk_sums, chunk_stride, bucket_sums);
-    if (cfg.msm_reduce2) k_reduce<2><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
-    else k_reduce<1><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
-    k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
+    if (coop) {
+        k_reduce_coop<<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
+        k_final_coop<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
+    } else {
+        k_reduce<1><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
+        k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
+    }
     B200_CUDA(cudaGetLastError());
     return 0;
 }

@@ -288,6 +288,25 @@ def evaluate_h(program: QuotientProgram, columns, k: int, ext_k: int) -> np.ndar
     return out
 
 
+def evaluate_h_from_polys(program: QuotientProgram, polys, domain, finish: bool = False) -> np.ndarray:
+    """b200_evaluate_h: columns given as the prover holds them — coefficient form (len < 2^ext_k: the library builds the coset) or already on
+    the extended domain (len == 2^ext_k).  `domain` is a halo2.EvaluationDomain; finish=True also divides by the vanishing polynomial
+    and returns the quotient's coefficients (all 2^ext_k of them)."""
+    nat.ensure_init()
+    cols = [nat.as_u64(c, 4) for c in polys]
+    N = 1 << domain.extended_k
+    lens = (C.c_size_t * max(1, len(cols)))(*[c.shape[0] for c in cols])
+    loads, consts, prog = program.arrays()
+    out = np.zeros((N, 4), np.uint64)
+    t_ev = nat.ptr(domain.t_evaluations) if finish else None
+    nat.check(nat.lib().b200_evaluate_h(nat.ptr_array(cols) if cols else None, lens, C.c_size_t(len(cols)), C.c_uint32(domain.k), C.c_uint32(domain.extended_k),
+                                        nat.ptr(domain.extended_omega), nat.ptr(domain.g_coset), loads.ctypes.data_as(C.c_void_p), C.c_size_t(loads.shape[0]),
+                                        nat.ptr(consts) if consts.size else None, C.c_size_t(consts.shape[0]), prog.ctypes.data_as(C.c_void_p), C.c_size_t(prog.shape[0]),
+                                        t_ev, C.c_uint32(domain.t_evaluations.shape[0] if finish else 0), nat.ptr(domain.extended_omega_inv) if finish else None,
+                                        nat.ptr(domain.extended_ifft_divisor) if finish else None, nat.ptr(out)))
+    return out
+
+
 def evaluate_h_device(program: QuotientProgram, columns, k: int, ext_k: int, out=None):
     """Device path: columns = list of torch int64 CUDA tensors [2^ext_k, 4]; enqueued on torch's current stream."""
     import torch

@@ -275,25 +275,25 @@ def create_proof(keys: Keys, advice, instances=(), rng=None, trace=None) -> byte
     for x, w_phi in zip(lk, phis_w):
         derived += [_wire(x["m"]), w_phi]
     polys = dom.lagrange_to_coeff_batch(derived)
-    cosets = dom.coeff_to_extended_batch(polys)
     na, nz = cs.num_advice, len(zs_w)
     adv_polys, z_polys = polys[:na], polys[na:na + nz]
     lk_polys = [(polys[na + nz + 2 * i], polys[na + nz + 2 * i + 1]) for i in range(len(lk))]
+    # evaluate_h at the CPU evaluator's own boundary: witness-derived columns go in coefficient form (the library builds their cosets), the
+    # key's cosets and the l-polynomials on the extended domain; one call also divides by the vanishing polynomial and converts back
     columns = [None] * L["count"]
     for i in range(na):
-        columns[i] = cosets[i]
+        columns[i] = adv_polys[i]
     for i in range(cs.num_fixed):
         columns[na + i] = keys.fixed_cosets[i]
     for i, c in enumerate(L["sigma"]):
         columns[c] = keys.sigma_cosets[i]
     for i, c in enumerate(L["z"]):
-        columns[c] = cosets[na + i]
+        columns[c] = z_polys[i]
     for i, (mc, pc) in enumerate(L["lookup"]):
-        columns[mc], columns[pc] = cosets[na + nz + 2 * i], cosets[na + nz + 2 * i + 1]
+        columns[mc], columns[pc] = lk_polys[i]
     columns[L["l0"]], columns[L["l_last"]], columns[L["l_active"]], columns[L["x"]] = keys.l0, keys.l_last, keys.l_active, keys.x_coset
     prog = ev.QuotientProgram(cs.numerator(beta, gamma, y))
-    h_ext = dom.divide_by_vanishing_poly(ev.evaluate_h(prog, columns, k, dom.extended_k))
-    h = dom.extended_to_coeff(h_ext)
+    h = ev.evaluate_h_from_polys(prog, columns, dom, finish=True)[: n * dom.quotient_poly_degree]
     pieces = [np.ascontiguousarray(h[i * n:(i + 1) * n]) for i in range(dom.quotient_poly_degree)]
     for c in params.commit_batch(pieces):
         tr.write_ec_point(c)

@@ -178,6 +178,17 @@ int b200_quotient_eval(const b200_fr* const* columns, size_t n_columns, uint32_t
 int b200_quotient_eval_dev(const void* const* d_columns, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_col_ref* loads, size_t n_loads,
                            const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr, void* d_out, void* stream);
 
+/* evaluate_h at the boundary the CPU evaluator has (UPSTREAM plonk/evaluation.rs builds the advice / instance cosets itself from the
+ * coefficient-form polynomials; plonk/vanishing/prover.rs then divides by the vanishing polynomial and converts back): column i of the
+ * program is coeff_to_extended(polys[i]) when lengths[i] < 2^ext_k (coefficient form, zeta coset, zero padded) and polys[i] itself when
+ * lengths[i] == 2^ext_k (the key's fixed / permutation cosets, l0 / l_last / l_active_row, a running partial sum).  out = the numerator on
+ * the extended domain, or, when t_evaluations != NULL, extended_to_coeff(numerator * t_evaluations[i mod t_period]): the quotient's
+ * 2^ext_k coefficients.  A coefficient column crosses PCIe once (its n elements) instead of its coset twice.  All columns' cosets are
+ * resident during the call (n_columns * 2^ext_k * 32 B): split larger systems into partial sums carried as an extended column. */
+int b200_evaluate_h(const b200_fr* const* polys, const size_t* lengths, size_t n_columns, uint32_t k, uint32_t ext_k, const b200_fr* ext_omega, const b200_fr* zeta,
+                    const b200_col_ref* loads, size_t n_loads, const b200_fr* constants, size_t n_constants, const b200_instr* program, size_t n_instr,
+                    const b200_fr* t_evaluations, uint32_t t_period, const b200_fr* ext_omega_inv, const b200_fr* ext_ifft_divisor, b200_fr* out);
+
 /* ---- device / pinned memory helpers for callers without their own CUDA runtime ---------------------------------- */
 int b200_dev_alloc(void** d_ptr, size_t bytes);
 int b200_dev_alloc_on(int device_slot, void** d_ptr, size_t bytes);   /* multi-device process: allocate on device `device_slot` */

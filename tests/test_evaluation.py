@@ -99,6 +99,32 @@ def test_device_interpreter_vs_oracle():
 
 
 @pytest.mark.gpu
+def test_fused_evaluate_h_entry_equals_the_composition():
+    """b200_evaluate_h (coefficient columns in, cosets built on the device, optional divide + extended_to_coeff) against the same steps
+    done call by call: mixed column kinds (coefficient columns of two lengths, extended columns), ragged grouping, both finish modes."""
+    from ezkl_b200 import _native as nat
+    from ezkl_b200 import halo2 as h2
+    nat.init(-1)
+    rng = random.Random(31)
+    k = 9
+    n = 1 << k
+    dom = h2.EvaluationDomain(5, k)
+    N = 1 << dom.extended_k
+    coeffs = [orc.gen_scalars(n, seed=700 + i) for i in range(5)]
+    short = orc.gen_scalars(n // 2, seed=710)                           # a lower-degree polynomial: shorter coefficient vector
+    ext_cols = [orc.gen_scalars(N, seed=720 + i) for i in range(2)]
+    polys = [coeffs[0], ext_cols[0], coeffs[1], coeffs[2], short, ext_cols[1], coeffs[3], coeffs[4]]
+    short_padded = np.concatenate([short, np.zeros((n - n // 2, 4), np.uint64)])
+    cosets = [dom.coeff_to_extended(p) if p.shape[0] == n else (dom.coeff_to_extended(short_padded) if p.shape[0] == n // 2 else p) for p in polys]
+    prog = ev.QuotientProgram(random_expr(rng, len(polys), 7) + ev.Query(4, 1) * ev.Query(5, -2))
+    num = ev.evaluate_h(prog, cosets, k, dom.extended_k)
+    assert np.array_equal(ev.evaluate_h_from_polys(prog, polys, dom), num)
+    want = dom.extended_to_coeff(dom.divide_by_vanishing_poly(num))
+    got = ev.evaluate_h_from_polys(prog, polys, dom, finish=True)
+    assert np.array_equal(got[: want.shape[0]], want)
+
+
+@pytest.mark.gpu
 def test_quotient_pipeline_on_a_satisfied_gate():
     """End-to-end property on a tiny PLONK-style circuit (q_m*a*b + q_c - c = 0 on every row, plus a rotation term
     a(wX) - d = 0): the GPU pipeline iNTT -> coset NTT -> evaluate_h -> divide_by_vanishing -> extended_to_coeff must give
