@@ -231,6 +231,19 @@ def run_b200(args):
     d_ext = 1 << tr["ext_bits"]
     tinv_local = np.ascontiguousarray(np.stack([dom.t_evaluations[(rank + world * t) % d_ext] for t in range(max(1, d_ext // world))]))
 
+    coll = {"on": False, "events": []}
+
+    def timed_collective(fn):
+        """Runs a torch.distributed call; while the profiling pass is on, brackets it with CUDA events on the current stream."""
+        if not coll["on"]:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        coll["events"].append((e0, e1))
+        return r
+
     def quotient_stage(get_col, put_h):
         """Stages 6-7.  Coset NTTs are dealt by column; evaluate_h runs row-cyclic (row idx on rank idx mod world): since
         world divides 2^ext_bits every Rotation(r) = r * 2^ext_bits rows stays on its rank, so the only exchange is one
@@ -249,7 +262,7 @@ def run_b200(args):
                 send = [view[:, :, s_].contiguous() for s_ in range(world)]
                 counts = [len([j for j in gcols if par.column_owner(j, world) == q]) for q in range(world)]
                 recv = [torch.empty((counts[q], slab, 4), dtype=torch.int64, device="cuda") for q in range(world)]
-                dist.all_to_all(recv, send)
+                timed_collective(lambda: dist.all_to_all(recv, send))
                 by_col = {}
                 for q in range(world):
                     for i_, j in enumerate([j for j in gcols if par.column_owner(j, world) == q]):
@@ -264,7 +277,7 @@ def run_b200(args):
         dev.scale_cycle(h, tinv_local)
         if world > 1:
             parts = [torch.empty_like(h) for _ in range(world)]
-            dist.all_gather(parts, h)
+            timed_collective(lambda: dist.all_gather(parts, h))
             full = torch.stack(parts, dim=1).reshape(1, N_ext, 4).contiguous()      # idx = t*world + rank
         else:
             full = h.view(1, N_ext, 4)
@@ -328,7 +341,7 @@ def run_b200(args):
                 done += b
         pts = torch.cat(commits) if commits else torch.zeros((0, 16), dtype=torch.int64, device="cuda")
         if world > 1:
-            par.allgather_columns(pts, commit_counts)      # per-rank counts follow from the deal: no size exchange, no host sync
+            timed_collective(lambda: par.allgather_columns(pts, commit_counts))      # per-rank counts follow from the deal: no size exchange, no host sync
         return pts
 
     L = nat.lib()
@@ -517,9 +530,12 @@ def run_b200(args):
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     # ---- same steps again with per-kernel-class CUDA events (roofline leg; not part of `value`)
     nat.check(L.b200_profile_enable(1))
+    coll["on"] = True
     for _ in range(args.steps):
         step_device()
     barrier()
+    coll["on"] = False
+    coll_ms = sum(a.elapsed_time(b) for a, b in coll["events"]) / args.steps
     prof = {}
     for cls, name in ((0, "msm_accumulate"), (1, "msm_total"), (2, "ntt"), (4, "msm_recode"), (5, "msm_tail"), (6, "quotient_eval")):
         ms, cnt = C.c_double(0), C.c_uint64(0)
@@ -632,6 +648,8 @@ def run_b200(args):
         "ntt_elts_per_s": round(ntt_elts / world / (ntt_ms * 1e-3), 1) * world if ntt_ms > 0 else None,
         "msm_ms_per_step": round(msm_ms, 3), "ntt_ms_per_step": round(ntt_ms, 3),
         "kernel_class_ms_per_step": {name: round(v[0] / args.steps, 3) for name, v in prof.items()},
+        "collectives_ms_per_step": {"rank0_total": round(coll_ms, 3), "calls_per_step": len(coll["events"]) // max(1, args.steps),
+                                    "what": "all_to_all per evaluate_h column group, all_gather of h slabs, all_gather of commitments (CUDA events on rank 0's stream; includes waiting for the slowest rank)"},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -69,6 +69,9 @@ struct Ctx {
     QuotientWorkspace quot_ws;
     StagingRing ring;
     DevBuf stage_a, stage_b, stage_c, small;
+    // pinned bounce buffers for large pageable <-> device copies (two slots, pipelined against the DMA engine)
+    uint8_t* bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     // the scratch above is per thread, not per stream: a call on another stream first waits for the previous call's work
     cudaEvent_t last_ev = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -79,6 +82,7 @@ struct Ctx {
                           &stage_a, &stage_b, &stage_c, &small};
         for (DevBuf* b : bufs) b->release();
         ring.release(); poly_ws.ring.release(); quot_ws.ring.release();
+        for (int i = 0; i < 2; ++i) { if (bounce[i]) cudaFreeHost(bounce[i]); if (bounce_ev[i]) cudaEventDestroy(bounce_ev[i]); bounce[i] = nullptr; bounce_ev[i] = nullptr; }
         if (last_ev) cudaEventDestroy(last_ev);
         if (stream) cudaStreamDestroy(stream);
         last_ev = nullptr; stream = nullptr;
@@ -171,6 +175,94 @@ static size_t call_budget() {
 }
 // host Fr values arrive with 8-byte alignment (Rust / C callers); Fr is alignas(16), so always copy bytewise
 static inline Fr as_fr(const b200_fr* p) { Fr r; memcpy(&r, p, sizeof r); return r; }
+
+// ---- large host <-> device copies of PAGEABLE caller memory (what a Rust Vec<Fr> is) ------------------------------------------------
+// cudaMemcpyAsync from pageable memory runs at 6-7 GB/s on this box (one driver thread copying into its own staging buffer).  Here the
+// copy is cut into 16 MiB chunks that four host threads move into a pinned bounce buffer while the DMA engine drains the other one, so
+// the PCIe link (Gen5 x16) is fed at memcpy-pool speed.  Small copies keep the plain path.
+static constexpr size_t BOUNCE_BYTES = (size_t)16 << 20;
+struct HostSeg { uint8_t* p; size_t bytes; };          // one caller buffer (a column); a list of them maps onto ONE contiguous device range
+// copies bytes [lo, hi) of the virtual concatenation of `segs` between the caller's buffers and `flat` (the pinned slot, offset 0 = byte lo0)
+static void seg_copy_range(const HostSeg* segs, size_t nsegs, size_t lo0, size_t lo, size_t hi, uint8_t* flat, bool to_flat) {
+    size_t pos = 0;
+    for (size_t i = 0; i < nsegs && pos < hi; ++i) {
+        const size_t s0 = pos, s1 = pos + segs[i].bytes;
+        pos = s1;
+        if (s1 <= lo) continue;
+        const size_t a = lo > s0 ? lo : s0, b = hi < s1 ? hi : s1;
+        if (to_flat) memcpy(flat + (a - lo0), segs[i].p + (a - s0), b - a);
+        else memcpy(segs[i].p + (a - s0), flat + (a - lo0), b - a);
+    }
+}
+static void seg_copy_parallel(const HostSeg* segs, size_t nsegs, size_t lo, size_t hi, uint8_t* flat, bool to_flat) {
+    const int T = 4;
+    const size_t bytes = hi - lo;
+    if (bytes < ((size_t)2 << 20)) { seg_copy_range(segs, nsegs, lo, lo, hi, flat, to_flat); return; }
+    const size_t part = ((bytes / T) + 4095) & ~(size_t)4095;
+    std::thread th[T - 1];
+    for (int i = 1; i < T; ++i) {
+        const size_t a = lo + part * i, b = a + part < hi ? a + part : hi;
+        if (a < b) th[i - 1] = std::thread([=] { seg_copy_range(segs, nsegs, lo, a, b, flat, to_flat); });
+    }
+    seg_copy_range(segs, nsegs, lo, lo, lo + part < hi ? lo + part : hi, flat, to_flat);
+    for (int i = 1; i < T; ++i) if (th[i - 1].joinable()) th[i - 1].join();
+}
+static int bounce_ready(Ctx* c) {
+    if (c->bounce[0]) return 0;
+    for (int i = 0; i < 2; ++i) {
+        B200_CUDA(cudaMallocHost((void**)&c->bounce[i], BOUNCE_BYTES));
+        B200_CUDA(cudaEventCreateWithFlags(&c->bounce_ev[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+// caller buffers -> contiguous device range.  When the call returns every SOURCE has been read; the device copies are ordered on `st`.
+static int h2d_segments(Ctx* c, void* d_dst, const HostSeg* segs, size_t nsegs, cudaStream_t st) {
+    size_t total = 0;
+    for (size_t i = 0; i < nsegs; ++i) total += segs[i].bytes;
+    if (total < ((size_t)8 << 20)) {
+        size_t off = 0;
+        for (size_t i = 0; i < nsegs; ++i) { B200_CUDA(cudaMemcpyAsync((uint8_t*)d_dst + off, segs[i].p, segs[i].bytes, cudaMemcpyHostToDevice, st)); off += segs[i].bytes; }
+        return 0;
+    }
+    if (int rc = bounce_ready(c)) return rc;
+    int slot = 0;
+    for (size_t off = 0; off < total; off += BOUNCE_BYTES, slot ^= 1) {
+        const size_t nb = total - off < BOUNCE_BYTES ? total - off : BOUNCE_BYTES;
+        B200_CUDA(cudaEventSynchronize(c->bounce_ev[slot]));                       // the DMA that last read this slot is done
+        seg_copy_parallel(segs, nsegs, off, off + nb, c->bounce[slot], true);
+        B200_CUDA(cudaMemcpyAsync((uint8_t*)d_dst + off, c->bounce[slot], nb, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaEventRecord(c->bounce_ev[slot], st));
+    }
+    return 0;
+}
+// contiguous device range -> caller buffers.  Synchronous for the host: when the call returns the destinations hold the data.
+static int d2h_segments(Ctx* c, const void* d_src, const HostSeg* segs, size_t nsegs, cudaStream_t st) {
+    size_t total = 0;
+    for (size_t i = 0; i < nsegs; ++i) total += segs[i].bytes;
+    if (total < ((size_t)8 << 20)) {
+        size_t off = 0;
+        for (size_t i = 0; i < nsegs; ++i) { B200_CUDA(cudaMemcpyAsync(segs[i].p, (const uint8_t*)d_src + off, segs[i].bytes, cudaMemcpyDeviceToHost, st)); off += segs[i].bytes; }
+        B200_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+    if (int rc = bounce_ready(c)) return rc;
+    const size_t nchunks = (total + BOUNCE_BYTES - 1) / BOUNCE_BYTES;
+    for (size_t i = 0; i <= nchunks; ++i) {                                        // chunk i's DMA overlaps chunk i-1's host copy
+        if (i < nchunks) {
+            const size_t off = i * BOUNCE_BYTES, nb = total - off < BOUNCE_BYTES ? total - off : BOUNCE_BYTES;
+            B200_CUDA(cudaMemcpyAsync(c->bounce[i & 1], (const uint8_t*)d_src + off, nb, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaEventRecord(c->bounce_ev[i & 1], st));
+        }
+        if (i > 0) {
+            const size_t off = (i - 1) * BOUNCE_BYTES, nb = total - off < BOUNCE_BYTES ? total - off : BOUNCE_BYTES;
+            B200_CUDA(cudaEventSynchronize(c->bounce_ev[(i - 1) & 1]));
+            seg_copy_parallel(segs, nsegs, off, off + nb, c->bounce[(i - 1) & 1], false);
+        }
+    }
+    return 0;
+}
+static int h2d_one(Ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) { HostSeg s{(uint8_t*)const_cast<void*>(h_src), bytes}; return h2d_segments(c, d_dst, &s, 1, st); }
+static int d2h_one(Ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) { HostSeg s{(uint8_t*)h_dst, bytes}; return d2h_segments(c, d_src, &s, 1, st); }
 
 // XYZZ (host) -> normalised Jacobian, one shared inversion (Montgomery's trick over zz*zzz)
 static void normalize_host(const G1Xyzz* pts, size_t n, b200_g1_jac* out) {
@@ -321,10 +413,12 @@ static int msm_host_on(Ctx* c, const BaseSet* bs, const b200_fr* const* cols, si
     StreamScope ss(c, nullptr);
     for (size_t b0 = 0; b0 < count; b0 += sub) {
         const size_t nb = count - b0 < sub ? count - b0 : sub;
+        std::vector<HostSeg> segs(nb);
         for (size_t b = 0; b < nb; ++b) {
             B200_CHECK(cols[b0 + b], -1, "msm: scalars[%zu] is null", b0 + b);
-            B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + b * n, cols[b0 + b] + base_off, sizeof(Fr) * n, cudaMemcpyHostToDevice, ss.st));
+            segs[b] = HostSeg{(uint8_t*)const_cast<b200_fr*>(cols[b0 + b] + base_off), sizeof(Fr) * n};
         }
+        if (int rc = h2d_segments(c, c->stage_a.p, segs.data(), nb, ss.st)) return rc;
         if (int rc = msm_dev_on(c, bs, c->stage_a.as<Fr>(), n, n, nb, base_off, c->small.as<G1Xyzz>() + b0, ss.st)) return rc;
         if (b0 + nb < count) B200_CUDA(cudaStreamSynchronize(ss.st));      // the staging buffer is reused by the next sub-batch
     }
@@ -774,14 +868,15 @@ static int ntt_host_on(Ctx* c, const b200_fr* const* src, b200_fr* const* dst, s
     StreamScope ss(c, nullptr);
     for (size_t b0 = 0; b0 < batch; b0 += sub) {
         const size_t nb = batch - b0 < sub ? batch - b0 : sub;
+        std::vector<HostSeg> up(nb), down(nb);
         for (size_t p = 0; p < nb; ++p) {
             B200_CHECK(src[b0 + p] && dst[b0 + p], -1, "ntt: polynomial %zu is null", b0 + p);
-            B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + p * n_in, src[b0 + p], sizeof(Fr) * n_in, cudaMemcpyHostToDevice, ss.st));
+            up[p] = HostSeg{(uint8_t*)const_cast<b200_fr*>(src[b0 + p]), sizeof(Fr) * n_in};
+            down[p] = HostSeg{(uint8_t*)dst[b0 + p], sizeof(Fr) * N};
         }
+        if (int rc = h2d_segments(c, c->stage_a.p, up.data(), nb, ss.st)) return rc;
         if (int rc = ntt_call(c, c->stage_a.as<Fr>(), n_in, n_in, c->stage_b.as<Fr>(), c->stage_c.as<Fr>(), N, log_n, omega, pre, post, (int)nb, ss.st)) return rc;
-        for (size_t p = 0; p < nb; ++p)
-            B200_CUDA(cudaMemcpyAsync(dst[b0 + p], c->stage_c.as<Fr>() + p * N, sizeof(Fr) * N, cudaMemcpyDeviceToHost, ss.st));
-        B200_CUDA(cudaStreamSynchronize(ss.st));
+        if (int rc = d2h_segments(c, c->stage_c.p, down.data(), nb, ss.st)) return rc;
     }
     return 0;
 }
@@ -910,11 +1005,13 @@ int b200_poly_lincomb(const b200_fr* const* polys, const b200_fr* scalars, size_
     if (n == 0) return 0;
     if (c->stage_a.ensure(sizeof(Fr) * n * (count ? count : 1)) || c->stage_b.ensure(sizeof(Fr) * n)) return -2;
     std::vector<const void*> ptrs(count);
+    std::vector<HostSeg> up(count);
     for (size_t j = 0; j < count; ++j) {
         B200_CHECK(polys[j], -1, "poly_lincomb: polys[%zu] is null", j);
         ptrs[j] = c->stage_a.as<Fr>() + j * n;
-        B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + j * n, polys[j], sizeof(Fr) * n, cudaMemcpyHostToDevice, c->stream));
+        up[j] = HostSeg{(uint8_t*)const_cast<b200_fr*>(polys[j]), sizeof(Fr) * n};
     }
+    if (int rc = h2d_segments(c, c->stage_a.p, up.data(), count, c->stream)) return rc;
     if (int rc = b200_poly_lincomb_dev(ptrs.data(), scalars, count, n, c->stage_b.p, nullptr)) return rc;
     B200_CUDA(cudaMemcpyAsync(out, c->stage_b.p, sizeof(Fr) * n, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));
@@ -962,10 +1059,12 @@ int b200_poly_eval_batch(const b200_fr* const* polys, size_t n, const b200_fr* x
     B200_CHECK(polys && x && out, -1, "poly_eval: null pointer");
     if (batch == 0) return 0;
     if (c->stage_a.ensure(sizeof(Fr) * (n ? n : 1) * batch) || c->small.ensure(sizeof(Fr) * batch)) return -2;
+    std::vector<HostSeg> up(batch);
     for (size_t p = 0; p < batch; ++p) {
         B200_CHECK(n == 0 || polys[p], -1, "poly_eval: polys[%zu] is null", p);
-        if (n) B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + p * n, polys[p], sizeof(Fr) * n, cudaMemcpyHostToDevice, c->stream));
+        up[p] = HostSeg{(uint8_t*)const_cast<b200_fr*>(polys[p]), sizeof(Fr) * n};
     }
+    if (n) { if (int rc = h2d_segments(c, c->stage_a.p, up.data(), batch, c->stream)) return rc; }
     if (int rc = b200_poly_eval_batch_dev(c->stage_a.p, n, n, x, batch, c->small.p, nullptr)) return rc;
     B200_CUDA(cudaMemcpyAsync(out, c->small.p, sizeof(Fr) * batch, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));
@@ -1107,15 +1206,15 @@ int b200_quotient_eval(const b200_fr* const* columns, size_t n_columns, uint32_t
     const size_t N = (size_t)1 << ext_k;
     if (c->stage_a.ensure(sizeof(Fr) * N * (n_columns ? n_columns : 1)) || c->stage_b.ensure(sizeof(Fr) * N)) return -2;
     std::vector<const void*> ptrs(n_columns);
+    std::vector<HostSeg> up(n_columns);
     for (size_t i = 0; i < n_columns; ++i) {
         B200_CHECK(columns[i], -1, "quotient_eval: column %zu is null", i);
         ptrs[i] = c->stage_a.as<Fr>() + i * N;
-        B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + i * N, columns[i], sizeof(Fr) * N, cudaMemcpyHostToDevice, c->stream));
+        up[i] = HostSeg{(uint8_t*)const_cast<b200_fr*>(columns[i]), sizeof(Fr) * N};
     }
+    if (int rc = h2d_segments(c, c->stage_a.p, up.data(), n_columns, c->stream)) return rc;
     if (int rc = b200_quotient_eval_dev(ptrs.data(), n_columns, k, ext_k, loads, n_loads, constants, n_constants, program, n_instr, c->stage_b.p, nullptr)) return rc;
-    B200_CUDA(cudaMemcpyAsync(out, c->stage_b.p, sizeof(Fr) * N, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
-    return 0;
+    return d2h_one(c, out, c->stage_b.p, sizeof(Fr) * N, c->stream);
 }
 
 // evaluate_h at its natural boundary: the CPU evaluator receives coefficient-form polynomials and builds their cosets itself
@@ -1148,8 +1247,9 @@ int b200_evaluate_h(const b200_fr* const* polys, const size_t* lengths, size_t n
     std::vector<size_t> group;           // coefficient columns of equal length are transformed together
     auto flush = [&](size_t len) -> int {
         if (group.empty()) return 0;
-        for (size_t p = 0; p < group.size(); ++p)
-            B200_CUDA(cudaMemcpyAsync(c->stage_a.as<Fr>() + p * len, polys[group[p]], sizeof(Fr) * len, cudaMemcpyHostToDevice, ss.st));
+        std::vector<HostSeg> up(group.size());
+        for (size_t p = 0; p < group.size(); ++p) up[p] = HostSeg{(uint8_t*)const_cast<b200_fr*>(polys[group[p]]), sizeof(Fr) * len};
+        if (int rc = h2d_segments(c, c->stage_a.p, up.data(), up.size(), ss.st)) return rc;
         // transform into scratch-free destinations: each polynomial lands in its own column of `ext` (dst stride = distance between them is
         // irregular, so one launch per run of consecutive column indices)
         size_t p0 = 0;
@@ -1165,7 +1265,7 @@ int b200_evaluate_h(const b200_fr* const* polys, const size_t* lengths, size_t n
     };
     size_t cur_len = 0;
     for (size_t i = 0; i < n_columns; ++i) {
-        if (lengths[i] == N) { B200_CUDA(cudaMemcpyAsync(ext + i * N, polys[i], sizeof(Fr) * N, cudaMemcpyHostToDevice, ss.st)); continue; }
+        if (lengths[i] == N) { if (int rc = h2d_one(c, ext + i * N, polys[i], sizeof(Fr) * N, ss.st)) return rc; continue; }
         if (!group.empty() && (lengths[i] != cur_len || group.size() == sub)) { if (int rc = flush(cur_len)) return rc; }
         cur_len = lengths[i];
         group.push_back(i);
@@ -1182,9 +1282,7 @@ int b200_evaluate_h(const b200_fr* const* polys, const size_t* lengths, size_t n
         post.mode = 3; post.c[0] = d; post.c[1] = d * z2; post.c[2] = d * z;
         if (int rc = ntt_call(c, h, N, N, ext, h, N, ext_k, as_fr(ext_omega_inv), none, post, 1, ss.st)) return rc;      // `ext` is free again: scratch
     }
-    B200_CUDA(cudaMemcpyAsync(out, h, sizeof(Fr) * N, cudaMemcpyDeviceToHost, ss.st));
-    B200_CUDA(cudaStreamSynchronize(ss.st));
-    return 0;
+    return d2h_one(c, out, h, sizeof(Fr) * N, ss.st);
 }
 
 }  // extern "C"

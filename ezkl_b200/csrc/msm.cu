@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(TREE_THREADS) k_final(const G1Xyzz* __restrict
 
 // ---- four-lane cooperative variants of 10 / 11 (ec_coop.cuh): a quad of lanes is one logical thread, a CTA holds COOP_LT of them ----
 static constexpr int COOP_LT = TREE_THREADS / 4;
+static constexpr size_t COOP_MAX_BUCKETS = (size_t)3 << 15;
 DEV G1Xyzz block_sum_coop(G1Xyzz v, G1Xyzz* sh) {
     const unsigned lt = threadIdx.x >> 2, q = threadIdx.x & 3;
     if (q == 0) sh[lt] = v;
@@ -458,8 +459,9 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
     uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
     if (cfg.msm_reduce_m >= 1 && cfg.msm_reduce_m <= 4096) reduce_m = (uint32_t)cfg.msm_reduce_m;    // tuning override
-    const bool coop = cfg.msm_reduce2 == 0;               // B200_MSM_REDUCE2=1 falls back to the one-lane-per-thread tail
-    if (coop && reduce_m > 8) reduce_m = 16;             // four lanes per logical thread: 4x the warps for the same buckets per thread
+    // the four-lane cooperative tail shortens the dependent chain but pays redundant add / select / shuffle work in every lane: measured
+    // faster up to ~2 columns of 2^15 buckets, slower from 7 columns on (profiles/r02_msm_tail_coop_vs_single_lane.txt)
+    const bool coop = cfg.msm_reduce2 == 0 && (size_t)batch * nb <= COOP_MAX_BUCKETS;      // B200_MSM_REDUCE2=1: never
     const uint32_t nparts = div_up(div_up(nb, reduce_m), coop ? COOP_LT : TREE_THREADS);
 
     // counts region (zeroed every call): hist | cursor | len_hist | len_cursor | heavy
