@@ -1098,7 +1098,19 @@ int b200_prefix_scan_dev(int product, const void* d_a, size_t n, const b200_fr* 
     B200_CHECK(d_a && init && d_out, -1, "prefix_scan: null pointer");
     const Fr iv = as_fr(init);
     StreamScope ss(c, stream);
-    int rc = poly_prefix_scan(product != 0, reinterpret_cast<const Fr*>(d_a), n, &iv, reinterpret_cast<Fr*>(d_out), c->poly_ws, ss.st);
+    int rc = poly_prefix_scan(product != 0, reinterpret_cast<const Fr*>(d_a), n, n, &iv, reinterpret_cast<Fr*>(d_out), n, 1, c->poly_ws, ss.st);
+    if (!rc && n) g_launches += 3;
+    return rc;
+}
+int b200_prefix_scan_batch_dev(int product, const void* d_a, size_t a_stride, size_t n, size_t batch, const b200_fr* inits, void* d_out, size_t out_stride, void* stream) {
+    B200_ENTER(c, d_a);
+    B200_CHECK(d_a && inits && d_out, -1, "prefix_scan: null pointer");
+    B200_CHECK(batch <= 1 || (a_stride >= n && out_stride >= n), -1, "prefix_scan: column stride smaller than the column");
+    if (batch == 0) return 0;
+    std::vector<Fr> iv(batch);
+    memcpy(iv.data(), inits, sizeof(Fr) * batch);
+    StreamScope ss(c, stream);
+    int rc = poly_prefix_scan(product != 0, reinterpret_cast<const Fr*>(d_a), a_stride, n, iv.data(), reinterpret_cast<Fr*>(d_out), out_stride, (int)batch, c->poly_ws, ss.st);
     if (!rc && n) g_launches += 3;
     return rc;
 }

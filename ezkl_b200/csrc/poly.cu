@@ -225,8 +225,10 @@ template <bool PRODUCT> DEV Fr op_identity() { return PRODUCT ? fp_one<FrTag>() 
 template <bool PRODUCT> DEV Fr op_apply(const Fr& a, const Fr& b) { return PRODUCT ? a * b : a + b; }
 
 template <bool PRODUCT>
-__global__ void __launch_bounds__(TB) k_scan_block_totals(const Fr* __restrict__ a, size_t n, Fr* __restrict__ blk_tot) {
+__global__ void __launch_bounds__(TB) k_scan_block_totals(const Fr* __restrict__ a_all, size_t a_stride, size_t n, Fr* __restrict__ blk_tot_all, uint32_t nblk) {
     __shared__ Fr sh[TB];
+    const Fr* a = a_all + (size_t)blockIdx.y * a_stride;
+    Fr* blk_tot = blk_tot_all + (size_t)blockIdx.y * nblk;
     const size_t lo = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * CHUNK;
     Fr v = op_identity<PRODUCT>();
     if (lo < n) { const size_t hi = lo + CHUNK < n ? lo + CHUNK : n; for (size_t j = lo; j < hi; ++j) v = op_apply<PRODUCT>(v, fp_load(a + j)); }
@@ -234,8 +236,11 @@ __global__ void __launch_bounds__(TB) k_scan_block_totals(const Fr* __restrict__
     if (threadIdx.x == TB - 1) fp_store(blk_tot + blockIdx.x, v);
 }
 template <bool PRODUCT>
-__global__ void __launch_bounds__(1024) k_scan_block_prefixes(const Fr* __restrict__ blk_tot, uint32_t nblk, Fr init, Fr* __restrict__ blk_pre) {
+__global__ void __launch_bounds__(1024) k_scan_block_prefixes(const Fr* __restrict__ blk_tot_all, uint32_t nblk, const Fr* __restrict__ inits, Fr* __restrict__ blk_pre_all) {
     __shared__ Fr sh[1024];
+    const Fr* blk_tot = blk_tot_all + (size_t)blockIdx.x * nblk;
+    Fr* blk_pre = blk_pre_all + (size_t)blockIdx.x * nblk;
+    const Fr init = fp_load(inits + blockIdx.x);
     const uint32_t ipt = (nblk + blockDim.x - 1) / blockDim.x;
     const uint32_t lo = threadIdx.x * ipt, hi = min(lo + ipt, nblk);
     Fr v = op_identity<PRODUCT>();
@@ -245,8 +250,11 @@ __global__ void __launch_bounds__(1024) k_scan_block_prefixes(const Fr* __restri
     for (uint32_t u = lo; u < hi; ++u) { fp_store(blk_pre + u, run); run = op_apply<PRODUCT>(run, fp_load(blk_tot + u)); }
 }
 template <bool PRODUCT>
-__global__ void __launch_bounds__(TB) k_scan_apply(const Fr* __restrict__ a, size_t n, const Fr* __restrict__ blk_pre, Fr* __restrict__ out) {
+__global__ void __launch_bounds__(TB) k_scan_apply(const Fr* __restrict__ a_all, size_t a_stride, size_t n, const Fr* __restrict__ blk_pre_all, uint32_t nblk, Fr* __restrict__ out_all, size_t out_stride) {
     __shared__ Fr sh[TB];
+    const Fr* a = a_all + (size_t)blockIdx.y * a_stride;
+    const Fr* blk_pre = blk_pre_all + (size_t)blockIdx.y * nblk;
+    Fr* out = out_all + (size_t)blockIdx.y * out_stride;
     const size_t lo = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * CHUNK;
     const size_t hi = lo + CHUNK < n ? lo + CHUNK : n;
     Fr v = op_identity<PRODUCT>();
@@ -259,20 +267,30 @@ __global__ void __launch_bounds__(TB) k_scan_apply(const Fr* __restrict__ a, siz
     }
 }
 
-int poly_prefix_scan(bool product, const Fr* a, size_t n, const Fr* h_init, Fr* out, PolyWorkspace& ws, cudaStream_t st) {
-    if (n == 0) return 0;
+// `batch` independent columns a[p * a_stride ..] -> out[p * out_stride ..], one initial value each (h_inits: host array)
+int poly_prefix_scan(bool product, const Fr* a, size_t a_stride, size_t n, const Fr* h_inits, Fr* out, size_t out_stride, int batch, PolyWorkspace& ws, cudaStream_t st) {
+    if (n == 0 || batch == 0) return 0;
+    B200_CHECK(batch > 0 && batch <= 65535, -1, "prefix_scan: batch %d out of range", batch);
     const uint32_t nblk = div_up(n, TILE);
-    if (ws.scratch.ensure(sizeof(Fr) * (size_t)nblk * 2)) return -2;
+    if (ws.scratch.ensure(sizeof(Fr) * ((size_t)nblk * 2 + 1) * batch)) return -2;
     Fr* blk_tot = ws.scratch.as<Fr>();
-    Fr* blk_pre = blk_tot + nblk;
+    Fr* blk_pre = blk_tot + (size_t)nblk * batch;
+    Fr* d_init = blk_pre + (size_t)nblk * batch;
+    const Fr* staged = reinterpret_cast<const Fr*>(ws.ring.push(h_inits, sizeof(Fr) * batch, st));
+    if (!staged) {
+        B200_CUDA(cudaMemcpyAsync(d_init, h_inits, sizeof(Fr) * batch, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaStreamSynchronize(st));       // h_inits is the caller's temporary
+        staged = d_init;
+    }
+    const dim3 grid(nblk, batch);
     if (product) {
-        k_scan_block_totals<true><<<nblk, TB, 0, st>>>(a, n, blk_tot);
-        k_scan_block_prefixes<true><<<1, 1024, 0, st>>>(blk_tot, nblk, *h_init, blk_pre);
-        k_scan_apply<true><<<nblk, TB, 0, st>>>(a, n, blk_pre, out);
+        k_scan_block_totals<true><<<grid, TB, 0, st>>>(a, a_stride, n, blk_tot, nblk);
+        k_scan_block_prefixes<true><<<batch, 1024, 0, st>>>(blk_tot, nblk, staged, blk_pre);
+        k_scan_apply<true><<<grid, TB, 0, st>>>(a, a_stride, n, blk_pre, nblk, out, out_stride);
     } else {
-        k_scan_block_totals<false><<<nblk, TB, 0, st>>>(a, n, blk_tot);
-        k_scan_block_prefixes<false><<<1, 1024, 0, st>>>(blk_tot, nblk, *h_init, blk_pre);
-        k_scan_apply<false><<<nblk, TB, 0, st>>>(a, n, blk_pre, out);
+        k_scan_block_totals<false><<<grid, TB, 0, st>>>(a, a_stride, n, blk_tot, nblk);
+        k_scan_block_prefixes<false><<<batch, 1024, 0, st>>>(blk_tot, nblk, staged, blk_pre);
+        k_scan_apply<false><<<grid, TB, 0, st>>>(a, a_stride, n, blk_pre, nblk, out, out_stride);
     }
     B200_CUDA(cudaGetLastError());
     return 0;

@@ -19,8 +19,8 @@ int poly_scale_cycle(const Fr* a, const Fr* d_consts, uint32_t period, Fr* out, 
 int poly_eval(const Fr* coeffs, size_t stride, size_t n, const Fr* h_x, Fr* d_out, int batch, PolyWorkspace& ws, cudaStream_t st);
 // in place a[i] <- a[i]^-1 (zeros stay zero)  (ff::BatchInvert)
 int poly_batch_invert(Fr* a, size_t n, PolyWorkspace& ws, cudaStream_t st);
-// exclusive running product / sum: out[0] = init, out[i+1] = out[i] (op) a[i]
-int poly_prefix_scan(bool product, const Fr* a, size_t n, const Fr* h_init, Fr* out, PolyWorkspace& ws, cudaStream_t st);
+// exclusive running product / sum per column: out[p][0] = inits[p], out[p][i+1] = out[p][i] (op) a[p][i], p < batch
+int poly_prefix_scan(bool product, const Fr* a, size_t a_stride, size_t n, const Fr* h_inits, Fr* out, size_t out_stride, int batch, PolyWorkspace& ws, cudaStream_t st);
 // quotient of a(X) by (X - b): q has n-1 coefficients (kate_division)
 int poly_kate_division(const Fr* a, size_t n, const Fr* h_b, Fr* q, PolyWorkspace& ws, cudaStream_t st);
 

@@ -219,6 +219,19 @@ def prefix_scan(a: torch.Tensor, init, product: bool, out: torch.Tensor | None =
     return out
 
 
+def prefix_scan_batch(a: torch.Tensor, inits, product: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    """a [batch, n, 4]: one exclusive running product / sum per column in one call; inits host [batch, 4]."""
+    _chk(a, 4)
+    batch, n = a.shape[0], a.shape[1]
+    if out is None:
+        out = torch.empty_like(a)
+    iv = nat.as_u64(inits, 4)
+    assert iv.shape[0] == batch
+    nat.check(nat.lib().b200_prefix_scan_batch_dev(C.c_int(1 if product else 0), nat.dev(a.data_ptr()), C.c_size_t(n), C.c_size_t(n), C.c_size_t(batch), nat.ptr(iv),
+                                                   nat.dev(out.data_ptr()), C.c_size_t(n), _stream()))
+    return out
+
+
 def kate_division(a: torch.Tensor, b, out: torch.Tensor | None = None) -> torch.Tensor:
     _chk(a, 4)
     n = a.numel() // 4

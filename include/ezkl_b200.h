@@ -149,6 +149,9 @@ int b200_batch_invert_dev(void* d_a, size_t n, void* stream);
 /* out[0] = init, out[i+1] = out[i] (* or +) a[i]: permutation z(X) / mv-lookup phi(X) running columns */
 int b200_prefix_scan(int product, const b200_fr* a, size_t n, const b200_fr* init, b200_fr* out);
 int b200_prefix_scan_dev(int product, const void* d_a, size_t n, const b200_fr* init, void* d_out, void* stream);
+/* `batch` independent columns in one call (the mv-lookup grand sums of a proof are independent of each other; the permutation products are
+ * chained through last_z and are not): column p at d_a + p * a_stride elements, its result at d_out + p * out_stride, initial value inits[p] */
+int b200_prefix_scan_batch_dev(int product, const void* d_a, size_t a_stride, size_t n, size_t batch, const b200_fr* inits, void* d_out, size_t out_stride, void* stream);
 /* kate_division(a, b): quotient of a(X) by (X - b), n-1 coefficients */
 int b200_kate_division(const b200_fr* a, size_t n, const b200_fr* b, b200_fr* q);
 int b200_kate_division_dev(const void* d_a, size_t n, const b200_fr* b, void* d_q, void* stream);

@@ -86,3 +86,16 @@ def test_three_pass_transforms_ext_k23():
     full = orc.gen_scalars(1 << ext_k, seed=4001)
     back = dom.extended_to_coeff(full)                               # inverse with the zeta^-i / 2^-ext_k post-scale, 3 passes
     assert np.array_equal(back, orc.extended_to_coeff(full, ext_k, THREADS)[: back.shape[0]])
+
+
+def test_batched_prefix_scan_matches_per_column_oracle():
+    """b200_prefix_scan_batch_dev: the independent grand sums / products of a proof in one call (ragged size, distinct initial values)."""
+    from ezkl_b200 import device as dev
+    n, batch = 5000, 7
+    cols = np.stack([orc.gen_scalars(n, seed=5000 + i) for i in range(batch)])
+    inits = orc.gen_scalars(batch, seed=5100)
+    d = dev.from_host(cols)
+    for product in (False, True):
+        got = dev.to_host(dev.prefix_scan_batch(d, inits, product))
+        for i in range(batch):
+            assert np.array_equal(got[i], orc.prefix_scan(cols[i], inits[i], product)), (product, i)
