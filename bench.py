@@ -163,6 +163,10 @@ def run_b200(args):
 
     rank, world, local = par.init_distributed("nccl" if args.gpus > 1 else None)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    sim = args.simulate_rank_of > 1            # profiling aid: this ONE GPU plays rank 0 of an N-way run (same deal, same kernels, exchanges skipped)
+    if sim:
+        assert world == 1, "--simulate-rank-of runs on one GPU"
+        world = args.simulate_rank_of
     torch.cuda.set_device(local)
     nat.init(local)
     k = args.k
@@ -259,11 +263,15 @@ def run_b200(args):
             else:
                 ext_my = torch.empty((0, N_ext, 4), dtype=torch.int64, device="cuda")
             if world > 1:
-                view = ext_my.view(len(my), slab, world, 4)
-                send = [view[:, :, s_].contiguous() for s_ in range(world)]
+                packed = ext_my.view(len(my), slab, world, 4).permute(2, 0, 1, 3).contiguous()      # ONE strided copy: [destination rank][column][row][limb]
+                send = [packed[s_] for s_ in range(world)]
                 counts = [len([j for j in gcols if par.column_owner(j, world) == q]) for q in range(world)]
                 recv = [torch.empty((counts[q], slab, 4), dtype=torch.int64, device="cuda") for q in range(world)]
-                timed_collective(lambda: dist.all_to_all(recv, send))
+                if sim:     # no peers: the packing copies above are kept, the received slabs are stand-ins cut from this rank's own columns
+                    pool_ = torch.cat(send) if my else torch.zeros((1, slab, 4), dtype=torch.int64, device="cuda")
+                    recv = [pool_[torch.arange(counts[q], device="cuda") % pool_.shape[0]] if counts[q] else recv[q] for q in range(world)]
+                else:
+                    timed_collective(lambda: dist.all_to_all(recv, send))
                 by_col = {}
                 for q in range(world):
                     for i_, j in enumerate([j for j in gcols if par.column_owner(j, world) == q]):
@@ -278,7 +286,10 @@ def run_b200(args):
         dev.scale_cycle(h, tinv_local)
         if world > 1:
             parts = [torch.empty_like(h) for _ in range(world)]
-            timed_collective(lambda: dist.all_gather(parts, h))
+            if sim:
+                parts = [h] * world
+            else:
+                timed_collective(lambda: dist.all_gather(parts, h))
             full = torch.stack(parts, dim=1).reshape(1, N_ext, 4).contiguous()      # idx = t*world + rank
         else:
             full = h.view(1, N_ext, 4)
@@ -340,7 +351,7 @@ def run_b200(args):
                         dev.kate_division(v[i], xs[i], out=out_n[i][: n - 1])
                 done += b
         pts = torch.cat(commits) if commits else torch.zeros((0, 16), dtype=torch.int64, device="cuda")
-        if world > 1:
+        if world > 1 and not sim:
             timed_collective(lambda: par.allgather_columns(pts, commit_counts))      # per-rank counts follow from the deal: no size exchange, no host sync
         return pts
 
@@ -489,12 +500,12 @@ def run_b200(args):
         return h2d, d2h
 
     def barrier():
-        if world > 1:
+        if world > 1 and not sim:
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
+        if world == 1 or sim:
             return ms
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -524,6 +535,7 @@ def run_b200(args):
     for _ in range(args.steps):
         step_device()
     e1.record()
+    issue_ms = (time.time() - t_reg0) * 1e3 / args.steps     # host time to ENQUEUE a step (close to ms_per_step means the host issue rate is the limiter)
     barrier()
     sampler.mark(t_reg0, time.time())
     launches = nat.launch_count() - l0
@@ -570,7 +582,7 @@ def run_b200(args):
     # ---- N > 1: ONE process (rank 0) owning all N devices through b200_init_multi, same host-pointer trace; the library deals
     #      columns / splits bases / shards transforms itself (device workers).  The other ranks idle on the rendezvous store.
     in_process = None
-    if world > 1 and not args.no_host_pointer_e2e and ext_k <= 23:
+    if world > 1 and not sim and not args.no_host_pointer_e2e and ext_k <= 23:
         store = dist.distributed_c10d._get_default_store()
         if rank == 0:
             try:
@@ -628,7 +640,9 @@ def run_b200(args):
         "ms_per_step": round(ms_dev, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 limbs (254-bit Montgomery integers mod BN254 r/p)", "data": "synthetic",
         "config": make_config(k, tname),
-        "parallelism": "columns round-robin over %d GPU(s), one process per GPU" % world,
+        "parallelism": ("columns round-robin over %d GPU(s), one process per GPU" % world) if not sim else
+                       ("SIMULATED rank 0 of %d on one GPU: that rank's share of every stage, exchanges skipped — a profiling aid, not a bench value" % world),
+        "host_issue_ms_per_step": round(issue_ms, 3),
         "l2": "inputs larger than L2: %d MB of columns + %d MB tables per step" % (ncols * n * 32 >> 20, (2 * n * 64 * win) >> 20),
         "parity_checked": parity_ops is not None, "parity_ops": parity_ops,
         "e2e": {"value": round(ms_e2e / 1e3, 6), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
@@ -639,10 +653,13 @@ def run_b200(args):
                      "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes_per_launch), "avg_launch_ms": round(acc_ms / max(acc_cnt, 1), 4),
                      "kernel_share_of_step": round(acc_ms / args.steps / ms_dev, 4) if ms_dev > 0 else None,
-                     "issue_bound": {"what": "bucket additions (XYZZ += affine: 6 multiplies + 2 dedicated squarings (0.78 each) + one two-product multiply (1.5) + 7 add/sub = 9.46 multiply-equivalents in IMAD.WIDE work) per second against the measured "
-                                             "254-bit multiply ceiling of 67.5 G mulmod/s (profiles/r01_microbench_mulmod.txt)",
+                     "issue_bound": {"what": "the integer-multiply roofline of the SM: 16 32-bit product words / clk / sub-partition = 148 x 64 x 1.965 GHz = 18.6 T words/s (IMAD = 1 word, IMAD.WIDE = 2 words, "
+                                             "carries free; profiles/r02_pipe_probe2_carry_cost.txt).  One bucket addition (XYZZ += affine) = 6 multiplications x 264 words + one two-product multiplication "
+                                             "with a single reduction (392) + 2 squarings of 36 products (208 each) = 2392 words",
                                      "adds_per_s": round(my_msm_cols * n * win / (acc_ms / args.steps * 1e-3), 1) if acc_ms > 0 else None,
-                                     "frac": round(my_msm_cols * n * win * 9.46 / (acc_ms / args.steps * 1e-3) / 67.5e9, 4) if acc_ms > 0 else None},
+                                     "words_per_s": round(my_msm_cols * n * win * 2392 / (acc_ms / args.steps * 1e-3), 1) if acc_ms > 0 else None,
+                                     "peak_words_per_s": 148 * 64 * 1.965e9,
+                                     "frac": round(my_msm_cols * n * win * 2392 / (acc_ms / args.steps * 1e-3) / (148 * 64 * 1.965e9), 4) if acc_ms > 0 else None},
                      "note": "integer-issue bound (254-bit modular arithmetic), not HBM bound: see DESIGN.md"},
         "msm_pairs_per_s": round(pairs / world / (msm_ms * 1e-3), 1) * world if msm_ms > 0 else None,
         "ntt_elts_per_s": round(ntt_elts / world / (ntt_ms * 1e-3), 1) * world if ntt_ms > 0 else None,
@@ -655,7 +672,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(k, tname)
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1 and not sim:
         dist.barrier()
         dist.destroy_process_group()
 
@@ -792,6 +809,7 @@ def main():
     ap.add_argument("--no-parity-gate", action="store_true", help="skip the oracle comparison of the timed inputs (profiling runs only; the line says parity_checked: false)")
     ap.add_argument("--no-host-pointer-e2e", action="store_true")
     ap.add_argument("--profile-one-step", action="store_true", help="setup + one device step only (for ncu launch lists)")
+    ap.add_argument("--simulate-rank-of", type=int, default=0, help="profiling aid: run rank 0's share of an N-way run on ONE GPU (collectives skipped); the line is marked SIMULATED")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -36,6 +36,7 @@ static void read_config() {
     c.ntt_nofull = getenv("B200_NTT_NOFULL") != nullptr;
     c.msm_reduce_m = env_int("B200_MSM_REDUCE_M", 0);
     c.msm_reduce2 = env_int("B200_MSM_REDUCE2", 0);
+    c.msm_reduce_threads = env_int("B200_MSM_REDUCE_THREADS", 0);
     c.shard_min_logn = env_int("B200_SHARD_MIN_LOGN", 22);
     g_cfg = c;
 }

@@ -89,7 +89,8 @@ struct Config {
     int ntt_threads = 0;            // B200_NTT_THREADS (v1 pass)
     int ntt_nofull = 0;             // B200_NTT_NOFULL: two-level inter-pass twiddles even when the full table exists
     int msm_reduce_m = 0;           // B200_MSM_REDUCE_M
-    int msm_reduce2 = 0;            // B200_MSM_REDUCE2=1: one-lane-per-thread reduction tail instead of the four-lane cooperative one
+    int msm_reduce2 = 0;            // B200_MSM_REDUCE2=2: four-lane cooperative reduction tail for <= 3 columns (A/B runs)
+    int msm_reduce_threads = 0;     // B200_MSM_REDUCE_THREADS: CTA size of the bucket reduction (32 / 64 / 128 / 256), 0 = automatic
     int shard_min_logn = 22;        // B200_SHARD_MIN_LOGN: a single transform of at least this size is sharded across the devices
 };
 const Config& config();

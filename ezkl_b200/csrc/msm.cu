@@ -22,7 +22,7 @@
 namespace b200 {
 
 static constexpr int HEAVY_CHUNKS = 32;     // buckets with more chunks than this are summed by a whole block
-static constexpr int REDUCE_M_MAX = 32;      // buckets per thread in k_reduce: 8 for small batches (latency), 32 for large (work)
+static constexpr int REDUCE_M_MAX = 32;      // buckets per thread in k_reduce for large (work-bound) batches; small batches take fewer (latency)
 static constexpr int TREE_THREADS = 256;
 
 int msm_default_window(size_t n) {
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(1024) k_scan_buckets(const uint32_t* __restric
     if (threadIdx.x == 0) sh_max = 0;
     __syncthreads();
     const uint32_t col = blockIdx.x;
+    const uint32_t lc = 31u - (uint32_t)__clz(cap);            // cap is a power of two (pick_cap)
     const uint32_t* cnt = counts + (size_t)col * nbuckets;
     uint32_t* off = offs + (size_t)col * (nbuckets + 1);
     uint32_t* coff = chunk_offs + (size_t)col * (nbuckets + 1);
@@ -125,12 +126,38 @@ __global__ void __launch_bounds__(1024) k_scan_buckets(const uint32_t* __restric
     const uint32_t lo = threadIdx.x * ipt, hi = min(lo + ipt, nbuckets);
     uint32_t s = 0, cs = 0;
     uint32_t mx = 0;
-    for (uint32_t b = lo; b < hi; ++b) { uint32_t v = cnt[b]; s += v; cs += (v + cap - 1) / cap; mx = max(mx, v); }
+    // a thread's buckets are consecutive: 128-bit loads (independent, so they pipeline) when its run is a multiple of four
+    const bool vec = (ipt & 3u) == 0 && lo + ipt <= nbuckets;
+    if (vec) {
+        const uint4* c4 = reinterpret_cast<const uint4*>(cnt + lo);
+#pragma unroll 4
+        for (uint32_t q = 0; q < (ipt >> 2); ++q) {
+            const uint4 v = c4[q];
+            s += v.x + v.y + v.z + v.w;
+            cs += ((v.x + cap - 1) >> lc) + ((v.y + cap - 1) >> lc) + ((v.z + cap - 1) >> lc) + ((v.w + cap - 1) >> lc);
+            mx = max(max(mx, v.x), max(max(v.y, v.z), v.w));
+        }
+    } else {
+        for (uint32_t b = lo; b < hi; ++b) { uint32_t v = cnt[b]; s += v; cs += ((v + cap - 1) >> lc); mx = max(mx, v); }
+    }
     if (mx) atomicMax(&sh_max, mx);
     uint32_t tot, ctot;
     uint32_t ex = block_exclusive_scan(s, &tot);
     uint32_t cex = block_exclusive_scan(cs, &ctot);
-    for (uint32_t b = lo; b < hi; ++b) { uint32_t v = cnt[b]; off[b] = ex; coff[b] = cex; ex += v; cex += (v + cap - 1) / cap; }
+    if (vec) {
+        const uint4* c4 = reinterpret_cast<const uint4*>(cnt + lo);
+#pragma unroll 4
+        for (uint32_t q = 0; q < (ipt >> 2); ++q) {
+            const uint4 v = c4[q];
+            const uint32_t b = lo + 4 * q;
+            off[b] = ex; coff[b] = cex; ex += v.x; cex += ((v.x + cap - 1) >> lc);
+            off[b + 1] = ex; coff[b + 1] = cex; ex += v.y; cex += ((v.y + cap - 1) >> lc);
+            off[b + 2] = ex; coff[b + 2] = cex; ex += v.z; cex += ((v.z + cap - 1) >> lc);
+            off[b + 3] = ex; coff[b + 3] = cex; ex += v.w; cex += ((v.w + cap - 1) >> lc);
+        }
+    } else {
+        for (uint32_t b = lo; b < hi; ++b) { uint32_t v = cnt[b]; off[b] = ex; coff[b] = cex; ex += v; cex += ((v + cap - 1) >> lc); }
+    }
     if (threadIdx.x == 0) {
         off[nbuckets] = tot; coff[nbuckets] = ctot;
         // a column is "skewed" when some bucket holds far more than its share: only then is warp-level aggregation of the
@@ -245,12 +272,12 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const G1Affine* __restric
     }
 }
 
-// block-wide sum of one XYZZ point per thread; result valid in thread 0. blockDim.x == TREE_THREADS.
+// block-wide sum of one XYZZ point per thread; result valid in thread 0. blockDim.x is a power of two <= TREE_THREADS.
 DEV G1Xyzz block_sum(G1Xyzz v, G1Xyzz* sh) {
     sh[threadIdx.x] = v;
     __syncthreads();
 #pragma unroll 1
-    for (unsigned s = TREE_THREADS / 2; s > 0; s >>= 1) {
+    for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
         if (threadIdx.x < s) { v = g1_add(v, sh[threadIdx.x + s]); sh[threadIdx.x] = v; }
         __syncthreads();
     }
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(TREE_THREADS) k_final(const G1Xyzz* __restrict
     const uint32_t col = blockIdx.x;
     G1Xyzz acc = g1_xyzz_identity();
 #pragma unroll 1
-    for (uint32_t j = threadIdx.x; j < nparts; j += TREE_THREADS) acc = g1_add(acc, partials[(size_t)col * nparts + j]);
+    for (uint32_t j = threadIdx.x; j < nparts; j += blockDim.x) acc = g1_add(acc, partials[(size_t)col * nparts + j]);
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) out[col] = acc;
 }
@@ -457,12 +484,26 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const uint32_t cap = pick_cap(ent_stride * batch);
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
-    uint32_t reduce_m = (batch >= 8 && nb >= 8192) ? REDUCE_M_MAX : 8;
+    // Bucket reduction geometry.  A thread owns reduce_m consecutive buckets (2 * reduce_m dependent additions, then a small-multiple
+    // fix-up and a block tree).  Large batches are work bound: 32 buckets per thread, 256-thread CTAs (swept in round 1).  Small batches
+    // are bound by the LATENCY of that dependent chain: one warp alone on a scheduler takes ~3.8 us per group addition, two warps sharing
+    // it twice that, so the bucket count is spread over about one warp per SM sub-partition (148 x 4 x 32 threads) in 64-thread CTAs, which
+    // shortens the chain and uses every SM (profiles/r02_msm_small_batches_*.txt).
+    const size_t all_buckets = (size_t)batch * nb;
+    uint32_t reduce_m = REDUCE_M_MAX, reduce_threads = TREE_THREADS;
+    if (all_buckets / REDUCE_M_MAX < (size_t)148 * 256) {
+        reduce_m = 2;
+        while (reduce_m < (uint32_t)REDUCE_M_MAX && all_buckets / reduce_m > (size_t)148 * 4 * 32 * 3 / 2) reduce_m <<= 1;
+        reduce_threads = 64;
+    }
     if (cfg.msm_reduce_m >= 1 && cfg.msm_reduce_m <= 4096) reduce_m = (uint32_t)cfg.msm_reduce_m;    // tuning override
-    // the four-lane cooperative tail shortens the dependent chain but pays redundant add / select / shuffle work in every lane: measured
-    // faster up to ~2 columns of 2^15 buckets, slower from 7 columns on (profiles/r02_msm_tail_coop_vs_single_lane.txt)
-    const bool coop = cfg.msm_reduce2 == 0 && (size_t)batch * nb <= COOP_MAX_BUCKETS;      // B200_MSM_REDUCE2=1: never
-    const uint32_t nparts = div_up(div_up(nb, reduce_m), coop ? COOP_LT : TREE_THREADS);
+    if (cfg.msm_reduce_threads == 32 || cfg.msm_reduce_threads == 64 || cfg.msm_reduce_threads == 128 || cfg.msm_reduce_threads == 256) reduce_threads = (uint32_t)cfg.msm_reduce_threads;
+    // the four-lane cooperative tail (ec_coop.cuh) is kept as an opt-in (B200_MSM_REDUCE2=2) for A/B runs
+    const bool coop = cfg.msm_reduce2 == 2 && all_buckets <= COOP_MAX_BUCKETS;
+    if (coop) { reduce_m = cfg.msm_reduce_m >= 1 ? reduce_m : 8; reduce_threads = TREE_THREADS; }
+    const uint32_t nparts = div_up(div_up(nb, reduce_m), coop ? COOP_LT : reduce_threads);
+    uint32_t final_threads = 32;
+    while (final_threads < (uint32_t)TREE_THREADS && final_threads < nparts) final_threads <<= 1;
 
     // counts region (zeroed every call): hist | cursor | len_hist | len_cursor | heavy
     const size_t n_hist = (size_t)batch * nb, n_len = (size_t)batch * (cap + 1), n_heavy = (size_t)batch * heavy_stride;
@@ -517,8 +558,8 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
         k_reduce_coop<<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
         k_final_coop<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
     } else {
-        k_reduce<1><<<dim3(nparts, batch), TREE_THREADS, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
-        k_final<<<batch, TREE_THREADS, 0, st>>>(partials, nparts, d_out);
+        k_reduce<1><<<dim3(nparts, batch), reduce_threads, 0, st>>>(bucket_sums, nb, partials, nparts, reduce_m);
+        k_final<<<batch, final_threads, 0, st>>>(partials, nparts, d_out);
     }
     B200_CUDA(cudaGetLastError());
     return 0;

@@ -1,0 +1,25 @@
+#!/bin/bash
+# job B (1 GPU): validate the latency-shaped bucket reduction (parity tests), A/B small batches, simulated rank-of-8 step, integer-pipe probes
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_bench_shapes.py -m gpu -x -q -k "msm or srs or kzg or commit or bench or shapes or splitting or empty or reentrancy" 2>&1 | tail -5 | tee gpurun_out/r02_gputests_msm_tail.txt
+tools/experiments/pipe_probe2 > gpurun_out/r02_pipe_probe2.txt 2>&1
+grep -E "^(F|C|G|H|D|E)" gpurun_out/r02_pipe_probe2.txt | grep 2048
+python tools/bench_msm.py one 1,2,3,4,7,8,16,26,60 > gpurun_out/r02_msm_small_batches_after.txt 2>&1
+cat gpurun_out/r02_msm_small_batches_after.txt
+B200_MSM_REDUCE2=2 python tools/bench_msm.py one 1,2,3 > gpurun_out/r02_msm_small_batches_coop.txt 2>&1
+cat gpurun_out/r02_msm_small_batches_coop.txt
+for T in 32 128; do echo "reduce threads $T"; B200_MSM_REDUCE_THREADS=$T python tools/bench_msm.py one 1,4,8,16 2>&1 | tee -a gpurun_out/r02_msm_small_batches_threads.txt; done
+python bench.py --simulate-rank-of 8 --steps 10 --warmup 3 --no-cpu-baseline --no-host-pointer-e2e --no-parity-gate > gpurun_out/r02_sim_rank_of_8.json 2> gpurun_out/r02_sim_rank_of_8.err
+tail -c 300 gpurun_out/r02_sim_rank_of_8.err
+python - <<PY
+import json
+d = json.loads(open("gpurun_out/r02_sim_rank_of_8.json").read().strip().splitlines()[-1])
+print("sim8 value", d["value"], "issue", d["host_issue_ms_per_step"], "launches", d["gpu_launches"], "classes", d["kernel_class_ms_per_step"])
+PY
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-host-pointer-e2e > gpurun_out/r02_bench_k17_quick.json 2> gpurun_out/r02_bench_k17_quick.err
+tail -c 300 gpurun_out/r02_bench_k17_quick.err
+python - <<PY
+import json
+d = json.loads(open("gpurun_out/r02_bench_k17_quick.json").read().strip().splitlines()[-1])
+print("N=1 value", d["value"], "e2e", d["e2e"]["value"], "parity", d["parity_checked"], "classes", d["kernel_class_ms_per_step"])
+PY
