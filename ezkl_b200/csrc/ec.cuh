@@ -115,15 +115,21 @@ HD bool g1_is_on_curve(const G1Affine& p) {
     Fq three = one + one + one;
     return fp_eq(fp_sqr(p.y), fp_sqr(p.x) * p.x + three);
 }
-// k * p for small k (double-and-add, MSB first); used for the bucket-index weighting in the reduction.
+// k * p for small k; used for the bucket-index weighting in the reduction.  Fixed 2-bit windows over {p, 2p, 3p}: the lanes of a warp
+// carry different k, so a bit-by-bit double-and-add executes BOTH the doubling and the addition of every bit for the whole warp
+// (divergence); here every window costs two doublings and one addition whatever the digits are.
 HD G1Xyzz g1_mul_small(const G1Xyzz& p, uint32_t k) {
-    G1Xyzz acc = g1_xyzz_identity();
-    int top = 31;
-    while (top > 0 && !((k >> top) & 1)) --top;
+    if (k == 0) return g1_xyzz_identity();
+    const G1Xyzz p2 = g1_dbl(p), p3 = g1_add(p2, p);
+    int top = 30;
+    while (top > 0 && !((k >> top) & 3u)) top -= 2;
+    uint32_t d = (k >> top) & 3u;
+    G1Xyzz acc = d == 1 ? p : (d == 2 ? p2 : p3);
 #pragma unroll 1
-    for (int i = top; i >= 0; --i) {
-        acc = g1_dbl(acc);
-        if ((k >> i) & 1) acc = g1_add(acc, p);
+    for (int i = top - 2; i >= 0; i -= 2) {
+        acc = g1_dbl(g1_dbl(acc));
+        d = (k >> i) & 3u;
+        if (d) acc = g1_add(acc, d == 1 ? p : (d == 2 ? p2 : p3));
     }
     return acc;
 }

@@ -485,17 +485,17 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     const size_t chunk_stride = (size_t)nb + ent_stride / cap + 1;
     const uint32_t heavy_stride = (uint32_t)(ent_stride / ((size_t)cap * HEAVY_CHUNKS)) + 2;
     // Bucket reduction geometry.  A thread owns reduce_m consecutive buckets (2 * reduce_m dependent additions, then a small-multiple
-    // fix-up and a block tree).  Large batches are work bound: 32 buckets per thread, 256-thread CTAs (swept in round 1).  Small batches
-    // are bound by the LATENCY of that dependent chain: one warp alone on a scheduler takes ~3.8 us per group addition, two warps sharing
-    // it twice that, so the bucket count is spread over about one warp per SM sub-partition (148 x 4 x 32 threads) in 64-thread CTAs, which
-    // shortens the chain and uses every SM (profiles/r02_msm_small_batches_*.txt).
+    // fix-up and a block tree).  Large batches are work bound: 32 buckets per thread, 256-thread CTAs.  Small batches are bound by the
+    // LATENCY of that dependent chain (a lone warp needs ~7.5 us per group addition, about 1000 cycles per field multiplication, twice its
+    // throughput cost), so fewer buckets per thread and more, smaller CTAs win until the extra threads' fix-ups and tree levels cost more
+    // than the shorter chain saves.  The table is the measured optimum per total bucket count (profiles/r02_msm_tail_sweep.txt).
     const size_t all_buckets = (size_t)batch * nb;
     uint32_t reduce_m = REDUCE_M_MAX, reduce_threads = TREE_THREADS;
-    if (all_buckets / REDUCE_M_MAX < (size_t)148 * 256) {
-        reduce_m = 2;
-        while (reduce_m < (uint32_t)REDUCE_M_MAX && all_buckets / reduce_m > (size_t)148 * 4 * 32 * 3 / 2) reduce_m <<= 1;
-        reduce_threads = 64;
-    }
+    if (all_buckets <= ((size_t)1 << 15)) { reduce_m = 4; reduce_threads = 128; }
+    else if (all_buckets <= ((size_t)1 << 18)) { reduce_m = 8; reduce_threads = 128; }
+    else if (all_buckets <= ((size_t)5 << 17)) { reduce_m = 16; reduce_threads = 256; }
+    else if (all_buckets < ((size_t)37 << 15)) { reduce_m = 32; reduce_threads = 128; }
+    while (reduce_m > 1 && reduce_m > nb) reduce_m >>= 1;
     if (cfg.msm_reduce_m >= 1 && cfg.msm_reduce_m <= 4096) reduce_m = (uint32_t)cfg.msm_reduce_m;    // tuning override
     if (cfg.msm_reduce_threads == 32 || cfg.msm_reduce_threads == 64 || cfg.msm_reduce_threads == 128 || cfg.msm_reduce_threads == 256) reduce_threads = (uint32_t)cfg.msm_reduce_threads;
     // the four-lane cooperative tail (ec_coop.cuh) is kept as an opt-in (B200_MSM_REDUCE2=2) for A/B runs

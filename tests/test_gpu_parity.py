@@ -228,6 +228,29 @@ def test_msm_degenerate_inputs():
     b2.release()
 
 
+@pytest.mark.parametrize("batch", [1, 2, 8, 9, 20, 21, 36, 37])
+def test_msm_reduction_geometry_rows(batch):
+    """The bucket reduction picks (buckets per thread, CTA size) from batch x buckets (msm.cu, msm_run): every row of that table, both
+    sides of each threshold, with the bench's window (c = 16 -> 2^15 buckets per column) on a base vector small enough for the oracle.
+    Scalars mix uniform columns with the skewed ones that leave most buckets empty or one bucket heavy."""
+    n = 1 << 11
+    bases_np = orc.gen_bases(n, seed=901)
+    bases = h2.Bases(bases_np, window_bits=16)
+    rng = random.Random(batch)
+    cols = []
+    for j in range(batch):
+        if j % 5 == 3:
+            cols.append(H.fr_array([rng.randrange(1 << 10) for _ in range(n)]))
+        elif j % 5 == 4:
+            cols.append(H.fr_array([pyref.R - 1 - (i % 3) for i in range(n)]))
+        else:
+            cols.append(orc.gen_scalars(n, seed=1000 * batch + j))
+    got = jac_to_affine(h2.best_multiexp_batch(cols, bases))
+    for j in sorted(set([0, 3, 4, batch // 2, batch - 1]) & set(range(batch))):
+        assert np.array_equal(got[j], orc.msm(cols[j], bases_np, THREADS)), (batch, j)
+    bases.release()
+
+
 def test_msm_k17_and_linearity_k20():
     """k = 17 (BASELINE configs[1]) against the oracle; k = 20 (configs[2]) through linearity + a k=20 oracle run."""
     n = 1 << 17
