@@ -169,6 +169,10 @@ def run_b200(args):
         world = args.simulate_rank_of
     torch.cuda.set_device(local)
     nat.init(local)
+    # all work of the trace is enqueued on one high-priority stream (the side stream of the two-stream schedule has the lowest priority,
+    # so its transforms only take what the main chain leaves idle); CUDA events below are recorded on this stream
+    prio_main, prio_side = [int(x) for x in os.environ.get("BENCH_STREAM_PRIORITIES", "-1,0").split(",")]      # tuning knob (A/B runs)
+    torch.cuda.set_stream(torch.cuda.Stream(priority=prio_main))
     k = args.k
     n = 1 << k
     tname = args.trace or CONFIG_FOR_K.get(k, "conv2d_mnist")
@@ -249,15 +253,65 @@ def run_b200(args):
         coll["events"].append((e0, e1))
         return r
 
-    def quotient_stage(get_col, put_h):
+    # ---- two-stream schedule -------------------------------------------------------------------------------------------------
+    # The iNTT and coset NTT of a witness-only column (advice, instance) depend on no transcript challenge, so a prover may run them any
+    # time after witness generation.  The MSM phases spend ~11 ms of a k = 17 step in latency-bound kernels (digit recoding, bucket
+    # reduction: few warps, the multiply pipe mostly idle), so those transforms are enqueued from a second host thread on a low-priority
+    # side stream and fill the idle pipe; the quotient stage waits for them.  Nothing of step i+1 starts before step i has finished
+    # (the side stream waits for an event recorded at the start of the step; the step ends by joining the side stream).
+    n_early = tr["advice"] + tr["instance"]                      # coset columns [0, n_early) are witness-only
+    q_groups = []
+    for g0 in range(0, ncoset, group):
+        gcols = list(range(g0, min(ncoset, g0 + group)))
+        my = [j for j in gcols if par.column_owner(j, world) == rank]
+        q_groups.append((gcols, my, len([j for j in my if j < n_early])))
+    my_ext_bytes = sum(len(my) for _, my, _ in q_groups) * N_ext * 32
+    overlap = (not args.no_overlap) and my_ext_bytes <= (24 << 30)
+    ov = {"bufs": None}
+    if overlap:
+        import concurrent.futures
+        ov["pool"] = concurrent.futures.ThreadPoolExecutor(1)
+        ov["stream"] = torch.cuda.Stream(priority=prio_side)    # default: lowest priority; the main work runs on a high-priority stream
+        ov["start"], ov["done"] = torch.cuda.Event(), torch.cuda.Event()
+        ov["bufs"] = [torch.empty((len(my), N_ext, 4), dtype=torch.int64, device="cuda") for _, my, _ in q_groups]
+        ne_max = max([ne for _, _, ne in q_groups] + [1])
+        ov["tmp"] = torch.empty((ne_max, N_ext, 4), dtype=torch.int64, device="cuda")
+        ov["side_out"] = torch.empty((ncols, n, 4), dtype=torch.int64, device="cuda")
+        ov["side_tmp"] = torch.empty((ncols, n, 4), dtype=torch.int64, device="cuda")
+
+    def early_transforms(cols_, n_intt_early, wait_events):
+        """Side thread: iNTT of this rank's witness-only columns, then their coset NTTs straight into the quotient stage's buffers."""
+        torch.cuda.set_device(local)
+        with torch.cuda.stream(ov["stream"]):
+            ov["stream"].wait_event(ov["start"])
+            for e_ in wait_events:
+                ov["stream"].wait_event(e_)
+            done = 0
+            while done < n_intt_early:
+                b = min(n_intt_early - done, ncols)
+                dev.ntt(cols_[:b], k, dom.omega_inv, post=[dom.ifft_divisor], out=ov["side_out"][:b], tmp=ov["side_tmp"][:b])
+                done += b
+            for gi, (gcols, my, ne) in enumerate(q_groups):
+                if ne:
+                    src = torch.stack([cols_[j % ncols] for j in my[:ne]])
+                    dev.ntt(src, ext_k, dom.extended_omega, n_in=n, pre=[one, zeta, zeta2], out=ov["bufs"][gi][:ne], tmp=ov["tmp"][:ne])
+            ov["done"].record(ov["stream"])
+
+    def quotient_stage(get_col, put_h, early=False):
         """Stages 6-7.  Coset NTTs are dealt by column; evaluate_h runs row-cyclic (row idx on rank idx mod world): since
         world divides 2^ext_bits every Rotation(r) = r * 2^ext_bits rows stays on its rank, so the only exchange is one
-        all-to-all per column group; h slabs are all-gathered once for the single extended iNTT on rank 0."""
+        all-to-all per column group; h slabs are all-gathered once for the single extended iNTT on rank 0.  With early=True the
+        witness-only columns of every group were already transformed on the side stream (early_transforms)."""
         h = torch.zeros((slab, 4), dtype=torch.int64, device="cuda")
-        for g0 in range(0, ncoset, group):
-            gcols = list(range(g0, min(ncoset, g0 + group)))
-            my = [j for j in gcols if par.column_owner(j, world) == rank]
-            if my:
+        if early:
+            torch.cuda.current_stream().wait_event(ov["done"])
+        for gi, (gcols, my, ne) in enumerate(q_groups):
+            if early:
+                ext_my = ov["bufs"][gi]
+                if len(my) > ne:
+                    src = torch.stack([get_col(j) for j in my[ne:]])
+                    dev.ntt(src, ext_k, dom.extended_omega, n_in=n, pre=[one, zeta, zeta2], out=ext_my[ne:])
+            elif my:
                 src = torch.stack([get_col(j) for j in my])
                 ext_my = dev.ntt(src, ext_k, dom.extended_omega, n_in=n, pre=[one, zeta, zeta2])
             else:
@@ -311,14 +365,28 @@ def run_b200(args):
     npolys_total = tr["advice"] + tr["fixed"] + tr["perm_cols"] + tr["perm_z"] + 2 * tr["lookups"] + 1 + tr["quotient_pieces"]
     lin_scalars = np.ascontiguousarray(np.tile(xs, (npolys_total // ncols + 1, 1))[:npolys_total])
 
-    def step_device(pool=None):
-        """One proof's trace with device-resident columns (pool defaults to the resident synthetic columns)."""
+    def step_device(pool=None, wait_events=(), serial=False):
+        """One proof's trace with device-resident columns (pool defaults to the resident synthetic columns).  serial=True runs the
+        whole trace on one stream in trace order (the per-kernel-class profiling pass needs non-overlapping kernels)."""
         cols_ = cols if pool is None else pool
         commits.clear()
         evals.clear()
+        two = overlap and not serial
+        fut = None
+        n_intt_early = 0
+        if two:
+            g_ = 0
+            for kind_, count_ in ops:
+                if kind_ == "intt":
+                    n_intt_early = len([i for i in mine(count_, g_) if i < n_early])
+                g_ += count_
+            ov["start"].record(torch.cuda.current_stream())
+            fut = ov["pool"].submit(early_transforms, cols_, n_intt_early, wait_events)
         gidx = 0
         for kind, count in ops:
             m = len(mine(count, gidx)) if kind != "quotient" else 1     # the quotient stage is cooperative: every rank takes part
+            if kind == "intt":
+                m -= n_intt_early                                         # those run on the side stream
             gidx += count
             done = 0
             while done < m:
@@ -339,7 +407,10 @@ def run_b200(args):
                 elif kind == "intt":
                     dev.ntt(v, k, dom.omega_inv, post=[dom.ifft_divisor], out=out_n[:b], tmp=tmp_n[:b])
                 elif kind == "quotient":
-                    quotient_stage(lambda j: cols_[j % ncols], None)
+                    if fut is not None:
+                        fut.result()                  # the side thread has ENQUEUED everything (its done event is recorded); no device sync
+                        fut = None
+                    quotient_stage(lambda j: cols_[j % ncols], None, early=two)
                 elif kind == "eval":
                     evals.append(dev.eval_batch(v, xs[:b]))
                 elif kind == "lincomb":
@@ -382,7 +453,7 @@ def run_b200(args):
                     upload_first.record(upload_stream)
             upload_done.record(upload_stream)
         torch.cuda.current_stream().wait_event(upload_first)
-        pts = step_device(e2e_pool)
+        pts = step_device(e2e_pool, wait_events=(upload_first,))
         torch.cuda.current_stream().wait_event(upload_done)
         jac = dev.normalize(pts)                                  # D2H of the XYZZ partials + host normalisation
         d2h += pts.numel() * 8
@@ -544,7 +615,7 @@ def run_b200(args):
     nat.check(L.b200_profile_enable(1))
     coll["on"] = True
     for _ in range(args.steps):
-        step_device()
+        step_device(serial=True)       # one stream, trace order: per-class event times must not overlap
     barrier()
     coll["on"] = False
     coll_ms = sum(a.elapsed_time(b) for a, b in coll["events"]) / args.steps
@@ -627,7 +698,10 @@ def run_b200(args):
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this same command (k = 17 only)
     traffic = None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_bench_step_k17.json")))["k_accumulate"]
+        cap_path = os.path.join(ROOT, "profiles", "r02_ncu_full_bench_step_k17.json")
+        if not os.path.exists(cap_path):
+            cap_path = os.path.join(ROOT, "profiles", "r01_ncu_full_bench_step_k17.json")
+        cap = json.load(open(cap_path))["k_accumulate"]
         if k == 17 and tname == "conv2d_mnist" and world == 1:
             rd, wr = cap["dram__bytes_read.sum"]["per_launch"], cap["dram__bytes_write.sum"]["per_launch"]
             traffic = int(sum(rd + wr) * 1e9 / len(rd))
@@ -643,6 +717,8 @@ def run_b200(args):
         "parallelism": ("columns round-robin over %d GPU(s), one process per GPU" % world) if not sim else
                        ("SIMULATED rank 0 of %d on one GPU: that rank's share of every stage, exchanges skipped — a profiling aid, not a bench value" % world),
         "host_issue_ms_per_step": round(issue_ms, 3),
+        "schedule": ("two streams: iNTT + coset NTT of the %d witness-only columns on a low-priority side stream (second host thread) while the commitment phases run; "
+                     "joined before evaluate_h; steps do not overlap each other" % n_early) if overlap else "one stream, trace order",
         "l2": "inputs larger than L2: %d MB of columns + %d MB tables per step" % (ncols * n * 32 >> 20, (2 * n * 64 * win) >> 20),
         "parity_checked": parity_ops is not None, "parity_ops": parity_ops,
         "e2e": {"value": round(ms_e2e / 1e3, 6), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
@@ -809,6 +885,7 @@ def main():
     ap.add_argument("--no-parity-gate", action="store_true", help="skip the oracle comparison of the timed inputs (profiling runs only; the line says parity_checked: false)")
     ap.add_argument("--no-host-pointer-e2e", action="store_true")
     ap.add_argument("--profile-one-step", action="store_true", help="setup + one device step only (for ncu launch lists)")
+    ap.add_argument("--no-overlap", action="store_true", help="single-stream schedule (trace order), for A/B against the two-stream schedule")
     ap.add_argument("--simulate-rank-of", type=int, default=0, help="profiling aid: run rank 0's share of an N-way run on ONE GPU (collectives skipped); the line is marked SIMULATED")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
