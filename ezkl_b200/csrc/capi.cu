@@ -37,7 +37,6 @@ static void read_config() {
     c.msm_reduce_m = env_int("B200_MSM_REDUCE_M", 0);
     c.msm_reduce2 = env_int("B200_MSM_REDUCE2", 0);
     c.msm_reduce_threads = env_int("B200_MSM_REDUCE_THREADS", 0);
-    c.msm_digit_ctas_per_sm = env_int("B200_MSM_DIGIT_CTAS_PER_SM", 0);
     c.shard_min_logn = env_int("B200_SHARD_MIN_LOGN", 22);
     g_cfg = c;
 }

@@ -90,7 +90,6 @@ struct Config {
     int ntt_nofull = 0;             // B200_NTT_NOFULL: two-level inter-pass twiddles even when the full table exists
     int msm_reduce_m = 0;           // B200_MSM_REDUCE_M
     int msm_reduce2 = 0;            // B200_MSM_REDUCE2=2: four-lane cooperative reduction tail for <= 3 columns (A/B runs)
-    int msm_digit_ctas_per_sm = 0;  // B200_MSM_DIGIT_CTAS_PER_SM: residency cap of the digit kernels (0 = none)
     int msm_reduce_threads = 0;     // B200_MSM_REDUCE_THREADS: CTA size of the bucket reduction (32 / 64 / 128 / 256), 0 = automatic
     int shard_min_logn = 22;        // B200_SHARD_MIN_LOGN: a single transform of at least this size is sharded across the devices
 };

@@ -536,10 +536,7 @@ int msm_run(const MsmTable& t, const Fr* d_scalars, size_t n, size_t stride, int
     ProfScope ps_total(PROF_MSM_TOTAL, st);
     B200_CUDA(cudaMemsetAsync(hist, 0, counts_words * 4, st));
     if (prof_enabled()) prof_mark(PROF_MSM_RECODE, st, true);
-    // digit kernels are bound by L2 atomics, not by the SM: cfg.msm_digit_ctas_per_sm caps their residency (grid-stride loop) so that a
-    // concurrent stream's CTAs (bench.py's side-stream transforms) find room on every SM while they run
-    unsigned dig_blocks = min(div_up(n, 256), 148u * 8u);
-    if (cfg.msm_digit_ctas_per_sm > 0) dig_blocks = min(dig_blocks, max(1u, 148u * (unsigned)cfg.msm_digit_ctas_per_sm / (unsigned)batch));
+    const unsigned dig_blocks = min(div_up(n, 256), 148u * 8u);
     dim3 gd(dig_blocks, batch);
     k_digits<false><<<gd, 256, 0, st>>>(d_scalars, stride, (uint32_t)n, (uint32_t)t.n, (uint32_t)base_off, c, W, nb, hist, nullptr, nullptr, 0, nullptr);
     k_scan_buckets<<<batch, 1024, 0, st>>>(hist, offs, chunk_offs, nb, cap, skew);
