@@ -279,22 +279,31 @@ def run_b200(args):
         ov["side_out"] = torch.empty((ncols, n, 4), dtype=torch.int64, device="cuda")
         ov["side_tmp"] = torch.empty((ncols, n, 4), dtype=torch.int64, device="cuda")
 
-    def early_transforms(cols_, n_intt_early, wait_events):
-        """Side thread: iNTT of this rank's witness-only columns, then their coset NTTs straight into the quotient stage's buffers."""
+    EARLY_CHUNK = 8          # columns per side-stream call when the columns are still arriving over PCIe (e2e leg)
+
+    def early_transforms(cols_, n_intt_early, ready):
+        """Side thread: iNTT of this rank's witness-only columns, then their coset NTTs straight into the quotient stage's buffers.
+        ready(slot) -> the CUDA event after which pool slot `slot` holds its column (e2e leg: the witness is still being uploaded, so the
+        work is cut into EARLY_CHUNK-column calls that start as soon as their columns have landed), or None when everything is resident."""
         torch.cuda.set_device(local)
         with torch.cuda.stream(ov["stream"]):
             ov["stream"].wait_event(ov["start"])
-            for e_ in wait_events:
-                ov["stream"].wait_event(e_)
+            step_cols = EARLY_CHUNK if ready is not None else ncols
             done = 0
             while done < n_intt_early:
-                b = min(n_intt_early - done, ncols)
-                dev.ntt(cols_[:b], k, dom.omega_inv, post=[dom.ifft_divisor], out=ov["side_out"][:b], tmp=ov["side_tmp"][:b])
+                b = min(n_intt_early - done, step_cols, ncols - done % ncols)
+                lo = done % ncols
+                if ready is not None:
+                    ov["stream"].wait_event(ready(lo + b - 1))
+                dev.ntt(cols_[lo:lo + b], k, dom.omega_inv, post=[dom.ifft_divisor], out=ov["side_out"][lo:lo + b], tmp=ov["side_tmp"][lo:lo + b])
                 done += b
             for gi, (gcols, my, ne) in enumerate(q_groups):
-                if ne:
-                    src = torch.stack([cols_[j % ncols] for j in my[:ne]])
-                    dev.ntt(src, ext_k, dom.extended_omega, n_in=n, pre=[one, zeta, zeta2], out=ov["bufs"][gi][:ne], tmp=ov["tmp"][:ne])
+                for a0 in range(0, ne, step_cols if ready is not None else max(ne, 1)):
+                    sub = my[a0:min(ne, a0 + (step_cols if ready is not None else ne))]
+                    if ready is not None:
+                        ov["stream"].wait_event(ready(max(j % ncols for j in sub)))
+                    src = torch.stack([cols_[j % ncols] for j in sub])
+                    dev.ntt(src, ext_k, dom.extended_omega, n_in=n, pre=[one, zeta, zeta2], out=ov["bufs"][gi][a0:a0 + len(sub)], tmp=ov["tmp"][:len(sub)])
             ov["done"].record(ov["stream"])
 
     def quotient_stage(get_col, put_h, early=False):
@@ -365,7 +374,7 @@ def run_b200(args):
     npolys_total = tr["advice"] + tr["fixed"] + tr["perm_cols"] + tr["perm_z"] + 2 * tr["lookups"] + 1 + tr["quotient_pieces"]
     lin_scalars = np.ascontiguousarray(np.tile(xs, (npolys_total // ncols + 1, 1))[:npolys_total])
 
-    def step_device(pool=None, wait_events=(), serial=False):
+    def step_device(pool=None, ready=None, serial=False):
         """One proof's trace with device-resident columns (pool defaults to the resident synthetic columns).  serial=True runs the
         whole trace on one stream in trace order (the per-kernel-class profiling pass needs non-overlapping kernels)."""
         cols_ = cols if pool is None else pool
@@ -381,7 +390,7 @@ def run_b200(args):
                     n_intt_early = len([i for i in mine(count_, g_) if i < n_early])
                 g_ += count_
             ov["start"].record(torch.cuda.current_stream())
-            fut = ov["pool"].submit(early_transforms, cols_, n_intt_early, wait_events)
+            fut = ov["pool"].submit(early_transforms, cols_, n_intt_early, ready)
         gidx = 0
         for kind, count in ops:
             m = len(mine(count, gidx)) if kind != "quotient" else 1     # the quotient stage is cooperative: every rank takes part
@@ -435,6 +444,7 @@ def run_b200(args):
     upload_stream = torch.cuda.Stream()
     upload_first = torch.cuda.Event()
     upload_done = torch.cuda.Event()
+    upload_chunk_ev = [torch.cuda.Event() for _ in range(e2e_pool.shape[0] // 8 + 2)]
 
     def step_host():
         """End to end through the C ABI from HOST buffers: every witness-derived column crosses PCIe once (b200_dev_upload from
@@ -449,11 +459,16 @@ def run_b200(args):
                 nat.check(L.b200_dev_upload_async(nat.dev(e2e_pool[slot].data_ptr()), C.c_void_p(host_cols[i % ncols].data_ptr()), C.c_size_t(n * 32),
                                                   C.c_void_p(upload_stream.cuda_stream)))
                 h2d += n * 32
+                if (slot + 1) % EARLY_CHUNK == 0 or slot == len(my_inputs) - 1:
+                    upload_chunk_ev[slot // EARLY_CHUNK].record(upload_stream)
                 if slot == min(ncols, len(my_inputs)) - 1:
                     upload_first.record(upload_stream)
             upload_done.record(upload_stream)
+        n_up = len(my_inputs)
+        # slot -> the event after which it is on the device (slots past the uploaded ones are resident stand-ins: the last event covers them)
+        ready = (lambda slot: upload_chunk_ev[min(slot, n_up - 1) // EARLY_CHUNK]) if n_up else None
         torch.cuda.current_stream().wait_event(upload_first)
-        pts = step_device(e2e_pool, wait_events=(upload_first,))
+        pts = step_device(e2e_pool, ready=ready)
         torch.cuda.current_stream().wait_event(upload_done)
         jac = dev.normalize(pts)                                  # D2H of the XYZZ partials + host normalisation
         d2h += pts.numel() * 8
