@@ -374,7 +374,7 @@ def run_b200(args):
     npolys_total = tr["advice"] + tr["fixed"] + tr["perm_cols"] + tr["perm_z"] + 2 * tr["lookups"] + 1 + tr["quotient_pieces"]
     lin_scalars = np.ascontiguousarray(np.tile(xs, (npolys_total // ncols + 1, 1))[:npolys_total])
 
-    def step_device(pool=None, ready=None, serial=False):
+    def step_device(pool=None, ready=None, serial=False, main_wait=None):
         """One proof's trace with device-resident columns (pool defaults to the resident synthetic columns).  serial=True runs the
         whole trace on one stream in trace order (the per-kernel-class profiling pass needs non-overlapping kernels)."""
         cols_ = cols if pool is None else pool
@@ -391,6 +391,8 @@ def run_b200(args):
                 g_ += count_
             ov["start"].record(torch.cuda.current_stream())
             fut = ov["pool"].submit(early_transforms, cols_, n_intt_early, ready)
+        if main_wait is not None:          # e2e leg: the commit chain needs the first batch of columns; the side stream (released above) does not
+            torch.cuda.current_stream().wait_event(main_wait)
         gidx = 0
         for kind, count in ops:
             m = len(mine(count, gidx)) if kind != "quotient" else 1     # the quotient stage is cooperative: every rank takes part
@@ -467,8 +469,7 @@ def run_b200(args):
         n_up = len(my_inputs)
         # slot -> the event after which it is on the device (slots past the uploaded ones are resident stand-ins: the last event covers them)
         ready = (lambda slot: upload_chunk_ev[min(slot, n_up - 1) // EARLY_CHUNK]) if n_up else None
-        torch.cuda.current_stream().wait_event(upload_first)
-        pts = step_device(e2e_pool, ready=ready)
+        pts = step_device(e2e_pool, ready=ready, main_wait=upload_first)
         torch.cuda.current_stream().wait_event(upload_done)
         jac = dev.normalize(pts)                                  # D2H of the XYZZ partials + host normalisation
         d2h += pts.numel() * 8
