@@ -92,6 +92,7 @@ def test_group_law_vs_oracle_including_degenerate_inputs():
     K = B.copy()
     ks = [rng.randrange(1 << 20) for _ in range(32)]
     ks[3], ks[4] = 0, 1
+    ks[5:16] = [2, 3, 4, 0xFFFFF, 0x55555, 0xAAAAA, 0xFFFFFFFF, 0x80000000, 0x40000000, 12, 0x30003]      # every 2-bit window digit, top windows, max
     for i, k in enumerate(ks):
         K[i, 0] = k
     nat.dbg_lib().b200_debug_host_g1_op(2, nat.ptr(A), nat.ptr(K), nat.ptr(out), n)
