@@ -9,7 +9,10 @@ for a circuit of the shape named in `config.workload`, on synthetic seeded colum
   * parity gate: BEFORE anything is timed, the exact timed inputs (the first batched MSM, the first batched iNTT, the first
                 coset-NTT group, its evaluate_h group and the evaluation batch) are compared byte for byte with the CPU oracle;
                 a mismatch aborts the run without printing a line (`parity_checked` in the line lists what was compared).
-  * `value`   : seconds per proof with all columns resident in HBM (device entry points), CUDA-event timed.
+  * `value`   : seconds per proof with all columns resident in HBM (device entry points), CUDA-event timed.  Schedule: one
+                high-priority stream in trace order, plus the iNTT / coset NTT of the witness-only columns (no transcript
+                challenge feeds them) on a low-priority side stream issued by a second host thread, joined before evaluate_h;
+                steps never overlap each other (`schedule` in the line; --no-overlap = everything on one stream).
   * `e2e`     : the same trace through the C ABI starting from pinned HOST buffers: each witness-derived column is uploaded
                 once, later stages use the device-pointer entry points (the resident-column shim of INTEGRATION.md §2b),
                 commitments are normalised on the host and evaluations read back; H2D/D2H and the host tail are timed.
@@ -22,6 +25,8 @@ for a circuit of the shape named in `config.workload`, on synthetic seeded colum
                 inside the library on the launching stream.
   * `cpu_baseline` / `--impl reference`: the CPU restatement of halo2's Rayon algorithms (oracle/, "port") running the WHOLE
                 trace for real on the box's host cores (a persistent thread pool, every op instance executed, nothing extrapolated).
+--simulate-rank-of N: ONE GPU executes rank 0's share of an N-way run (same deal, same kernels, exchanges skipped) so that a rank's
+per-step kernel list can be profiled without N GPUs; the line is marked SIMULATED and is not a bench value.
 N > 1 (torchrun): independent columns are dealt round-robin to ranks (strong scaling, no data-path collective inside an
 op; one small all-gather of the commitments per step), timed as max over ranks; rank 0 then also times the same trace with ONE
 process driving all N devices through the library's own multi-device host-pointer path (`in_process`).
