@@ -96,6 +96,88 @@ def eval_expr(e, value_of):
     return {"sum": lambda: v[0] + v[1], "sub": lambda: v[0] - v[1], "product": lambda: v[0] * v[1], "negated": lambda: -v[0]}[e.kind]() % R
 
 
+def int_columns_of_a_satisfying_system(rng, k, beta, gamma):
+    """Every column of the ezkl-shaped system as python ints on the base domain: the witness of build_witness, then m, Phi and the two
+    chained, blinded grand products restated directly from their definitions (no library call)."""
+    n = 1 << k
+    col, u = build_witness(rng, k)
+    t_default = col[TABLE][0]
+    f = [(col[SEL_L][i] * col[A1][i] + (1 - col[SEL_L][i]) * t_default) % R for i in range(n)]
+    first_row = {}
+    for i in range(u):
+        first_row.setdefault(col[TABLE][i], i)
+    for v in f[:u]:
+        col[M][first_row[v]] += 1
+    inv = lambda v: pow(v % R, -1, R)
+    phi = [0]
+    for i in range(u):
+        phi.append((phi[-1] + inv(f[i] + beta) - col[M][i] * inv(col[TABLE][i] + beta)) % R)
+    assert phi[u] == 0                                           # the logUp argument closes over the active rows
+    col[PHI] = phi + [rng.randrange(R) for _ in range(n - u - 1)]
+    for i in range(u, n):
+        col[M][i] = rng.randrange(R)
+    w = pyref.omega_for(k)
+    perm_cols = [A0, A1, B0, B1, OUT]
+    last_z = 1
+    for ci, zc in enumerate(Z):
+        cs = perm_cols[ci * CHUNK:(ci + 1) * CHUNK]
+        ss = SIG[ci * CHUNK:(ci + 1) * CHUNK]
+        z = [last_z]
+        for i in range(u):
+            num = den = 1
+            for j, (c, s_) in enumerate(zip(cs, ss)):
+                num = num * (col[c][i] + beta * pow(ev.DELTA, ci * CHUNK + j, R) * pow(w, i, R) + gamma) % R
+                den = den * (col[c][i] + beta * col[s_][i] + gamma) % R
+            z.append(z[-1] * num % R * inv(den) % R)
+        last_z = z[u]
+        col[zc] = z + [rng.randrange(R) for _ in range(n - u - 1)]
+    assert last_z == 1                                           # the permutation argument closes
+    # l0, l_last, l_active and the identity polynomial X on the base domain
+    for i in range(n):
+        col[L0][i] = 1 if i == 0 else 0
+        col[LLAST][i] = 1 if i == u else 0
+        col[LACT][i] = 1 if i < u else 0
+        col[XCOL][i] = pow(w, i, R)
+    return col, u, t_default
+
+
+def test_ezkl_shaped_system_vanishes_on_the_domain_and_detects_tampering():
+    """CPU-only pin of the term builders and the compiler on the whole ezkl-shaped system (BaseConfig gates, two-chunk blinded
+    permutation chained through last_z, one mv-lookup): with the grand products, the grand sum and the multiplicities restated in python
+    ints, the folded numerator is 0 on EVERY row of the base domain (tree semantics, the compiled program's integer evaluator, and the
+    oracle's interpreter agree), and a single tampered cell makes it non-zero on the rows that cell touches."""
+    rng = random.Random(77)
+    k = 5
+    n = 1 << k
+    beta, gamma, y = (rng.randrange(R) for _ in range(3))
+    col, u, t_default = int_columns_of_a_satisfying_system(rng, k, beta, gamma)
+    perm_cols = [A0, A1, B0, B1, OUT]
+    lookup_in = ev.Query(SEL_L) * ev.Query(A1) + (ev.Constant(1) - ev.Query(SEL_L)) * ev.Constant(t_default)
+    terms = ev.base_op_gates(SEL, [A0, A1], [B0, B1], OUT) + ev.permutation_terms(perm_cols, SIG, Z, L0, LLAST, LACT, XCOL, beta, gamma, CHUNK, BLIND) + \
+        ev.mv_lookup_terms([lookup_in], ev.Query(TABLE), M, PHI, L0, LLAST, LACT, beta)
+    expr = ev.fold_y(terms, y)
+    prog = ev.QuotientProgram(expr)
+    loads, consts, instrs = prog.arrays()
+    # every single term vanishes on every row (so the fold does, whatever y is)
+    for ti, t in enumerate(terms):
+        for i in range(n):
+            assert eval_expr(t, lambda c, rot: col[c][(i + rot) % n]) == 0, (ti, i)
+    got = H.fr_list(orc.quotient_eval([H.fr_array(c) for c in col], k, k, loads, consts, instrs, threads=2))     # ext_k = k: rotations step by one row
+    for i in range(n):
+        assert prog.evaluate_ints(col, i, n, 1) == 0 and got[i] == 0, i
+    # tamper with one active output cell: its own gate row, the row that accumulates from it, and the permutation rows break
+    bad = [list(c) for c in col]
+    bad[OUT][3] = (bad[OUT][3] + 1) % R
+    nz = [i for i in range(n) if prog.evaluate_ints(bad, i, n, 1) != 0]
+    assert 3 in nz and len(nz) >= 1
+    assert H.fr_list(orc.quotient_eval([H.fr_array(c) for c in bad], k, k, loads, consts, instrs, threads=2))[3] == prog.evaluate_ints(bad, 3, n, 1) != 0
+    # a wrong multiplicity breaks only the lookup's running-sum term
+    bad = [list(c) for c in col]
+    bad[M][0] = (bad[M][0] + 1) % R
+    broken = [ti for ti, t in enumerate(terms) if any(eval_expr(t, lambda c, rot: bad[c][(i + rot) % n]) != 0 for i in range(n))]
+    assert broken == [len(terms) - 1]
+
+
 @pytest.mark.gpu
 def test_ezkl_shaped_constraint_system_through_evaluate_h():
     from ezkl_b200 import _native as nat
