@@ -225,6 +225,61 @@ def test_permutation_product_and_lookup_sum():
     assert phi == exp and acc == 0
 
 
+def test_shplonk_host_logic_on_the_cpu_backend(monkeypatch):
+    """The SHPLONK mirror's host logic (rotation sets, interpolants, ASCENDING powers of y and v, linearisation at u) with the
+    polynomial steps executed by the CPU oracle (tests/cpu_backend.py): every rotation set's quotient divides exactly, L(u) == 0, and
+    VerifierSHPLONK's equation holds in scalar form at the trapdoor.  With DESCENDING powers (the GWC rule) the same equation fails —
+    the ordering is what this pins."""
+    from ezkl_b200 import multiopen as mo
+    from tests import cpu_backend as cb
+    monkeypatch.setattr(mo, "h2", cb)
+    rng = random.Random(43)
+    k = 6
+    n = 1 << k
+    s = rng.randrange(2, R)
+    params = cb.TrapdoorParams(k, s)
+    w = pyref.omega_for(k)
+    x = rng.randrange(R)
+    polys = [orc.gen_scalars(n, seed=700 + i) for i in range(5)]
+    pts_a, pts_b, pts_c = [x, x * w % R], [x], [x, x * w % R, x * pow(w, -1, R) % R]
+    queries = []
+    for p, pts in ((polys[0], pts_a), (polys[1], pts_b), (polys[2], pts_a), (polys[3], pts_c), (polys[4], pts_b)):
+        queries += [mo.ProverQuery(pt, p) for pt in pts]
+    y, v, u = (rng.randrange(R) for _ in range(3))
+    prf = mo.create_proof(params, queries, y, v, u)
+    assert prf["must_be_zero"] == 0
+    assert [len(pl) for _, pl in prf["sets"]] == [2, 2, 1] and len(prf["super_points"]) == 3
+    sv = H.fr_wire(s)
+    evs = lambda poly: H.fr_unwire(cb.eval_polynomial(poly, sv))
+    # the set quotients divide exactly: q_i(z) * Z_i(z) == N_i(z) at a random z, and h = sum v^i q_i
+    z = rng.randrange(R)
+    ez = lambda poly: H.fr_unwire(cb.eval_polynomial(poly, H.fr_wire(z)))
+    acc = 0
+    for i, ((points, _), num) in enumerate(zip(prf["sets"], prf["numerators"])):
+        acc = (acc + pow(v, i, R) * ez(num) * pow(mo.evaluate_vanishing_polynomial(points, z), -1, R)) % R
+    assert ez(prf["h_x"]) == acc and ez(prf["h2_x"]) * (z - u) % R == ez(prf["l_x"])
+
+    def verifier_rhs(y_pows, v_pows):
+        zt = mo.evaluate_vanishing_polynomial(prf["super_points"], u)
+        z0_inv = pow(prf["z_diffs"][0], -1, R)
+        outer = 0
+        for i, ((points, polys_i), r_polys, zd) in enumerate(zip(prf["sets"], prf["r_polys"], prf["z_diffs"])):
+            inner = 0
+            for j, (pl, rp) in enumerate(zip(polys_i, r_polys)):
+                r_u = sum(c * pow(u, t, R) for t, c in enumerate(rp)) % R
+                inner = (inner + y_pows(j, len(polys_i)) * (evs(pl) - r_u)) % R
+            outer = (outer + v_pows(i, len(prf["sets"])) * zd % R * z0_inv % R * inner) % R
+        return (outer - zt * z0_inv % R * evs(prf["h_x"])) % R
+
+    lhs = evs(prf["h2_x"]) * (s - u) % R
+    assert lhs == verifier_rhs(lambda j, m: pow(y, j, R), lambda i, m: pow(v, i, R))                      # ascending: SHPLONK
+    assert lhs != verifier_rhs(lambda j, m: pow(y, m - 1 - j, R), lambda i, m: pow(v, m - 1 - i, R))      # descending: GWC's fold
+    # the commitments are the trapdoor evaluations of the polynomials behind them
+    G = np.array(list(H.fq_wire(1)) + list(H.fq_wire(2)), np.uint64).reshape(1, 8)
+    assert np.array_equal(prf["h1"][:8], orc.g1_scalar_mul(G, H.fr_array([evs(prf["h_x"])]))[0])
+    assert np.array_equal(prf["h2"][:8], orc.g1_scalar_mul(G, H.fr_array([evs(prf["h2_x"])]))[0])
+
+
 @pytest.mark.gpu
 def test_shplonk_multiopen_flow_with_known_trapdoor():
     """ProverSHPLONK mirror (ezkl_b200/multiopen.py) composed from the device primitives, on an SRS whose trapdoor s is known:
