@@ -107,6 +107,40 @@ def test_constraint_system_shape():
     assert L["sigma"] == tcs.SIG and L["z"] == tcs.Z and L["lookup"] == [(tcs.M, tcs.PHI)] and L["x"] == tcs.XCOL and L["count"] == tcs.NCOLS
 
 
+def test_prove_and_verify_round_trip_on_the_cpu_backend(monkeypatch):
+    """The create_proof mirror end to end WITHOUT a GPU: transcript, rng, blinding, commit phases, multiplicities, chained grand products,
+    grand sum, quotient, evaluations and SHPLONK run as host logic, every polynomial-sized primitive redirected to the CPU oracle
+    (tests/cpu_backend.patch_backend).  The proof verifies against the restated verifier at the trapdoor, is deterministic, and every
+    rejection case of the GPU test rejects here too."""
+    from tests import cpu_backend as cb
+    cb.patch_backend(monkeypatch)
+    rng = random.Random(123)
+    k = 6
+    s = rng.randrange(2, R)
+    params = cb.FullTrapdoorParams(k, s)
+    cs, fixed, sigmas, advice = build_system(rng, k)
+    keys = pv.Keys(params, cs, fixed, sigmas, vk_repr=0x77)
+    trace = {}
+    proof = pv.create_proof(keys, advice, rng=pv.ChaCha12Rng(bytes(32)), trace=trace)
+    n_pts = 5 + 1 + 2 + 1 + 1 + keys.domain.quotient_poly_degree
+    n_sc = len(cs.advice_queries) + len(cs.fixed_queries) + 1 + 5 + (3 + 2) + 3
+    assert len(proof) == 64 * (n_pts + 2) + 32 * n_sc
+    assert pv.verify_proof_with_trapdoor(keys, proof, s)
+    assert pv.create_proof(keys, advice, rng=pv.ChaCha12Rng(bytes(32))) == proof                 # deterministic (det-prove rng)
+    assert pv.create_proof(keys, advice, rng=pv.ChaCha12Rng(bytes([1] * 32))) != proof           # the blinding comes from the rng
+    bad = bytearray(proof)
+    bad[64 * n_pts + 31] ^= 1
+    assert not pv.verify_proof_with_trapdoor(keys, bytes(bad), s)                               # a flipped evaluation
+    bad = bytearray(proof)
+    bad[40] ^= 1
+    assert not pv.verify_proof_with_trapdoor(keys, bytes(bad), s)                               # a flipped commitment coordinate
+    assert not pv.verify_proof_with_trapdoor(keys, proof, (s + 1) % R)                          # the wrong trapdoor
+    assert not pv.verify_proof_with_trapdoor(keys, proof[:-32], s)                              # a truncated proof
+    advice_bad = [list(c) for c in advice]
+    advice_bad[tcs.OUT][3] = (advice_bad[tcs.OUT][3] + 1) % R
+    assert not pv.verify_proof_with_trapdoor(keys, pv.create_proof(keys, advice_bad, rng=pv.ChaCha12Rng(bytes(32))), s)    # an unsatisfied gate
+
+
 @pytest.mark.gpu
 def test_prove_and_verify_round_trip_with_trapdoor_srs():
     from ezkl_b200 import _native as nat
