@@ -141,6 +141,45 @@ def test_prove_and_verify_round_trip_on_the_cpu_backend(monkeypatch):
     assert not pv.verify_proof_with_trapdoor(keys, pv.create_proof(keys, advice_bad, rng=pv.ChaCha12Rng(bytes(32))), s)    # an unsatisfied gate
 
 
+GOLDEN_PROOF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mirror_proof_k6.bin")
+
+
+def golden_case():
+    """The fixed case behind tests/golden/mirror_proof_k6.bin: trapdoor, ezkl-shaped system and witness from one seeded generator, the
+    det-prove rng (ChaCha12, zero seed)."""
+    rng = random.Random(20260923)
+    k = 6
+    s = rng.randrange(2, R)
+    cs, fixed, sigmas, advice = build_system(rng, k)
+    return k, s, cs, fixed, sigmas, advice
+
+
+def test_cpu_backend_proof_equals_the_golden_bytes(monkeypatch):
+    """The proof the mirror emits with every primitive on the CPU oracle is the committed golden (regenerate with
+    `python tests/test_prover_mirror.py --regenerate` only when the mirror's transcript / rng order changes on purpose)."""
+    from tests import cpu_backend as cb
+    cb.patch_backend(monkeypatch)
+    k, s, cs, fixed, sigmas, advice = golden_case()
+    keys = pv.Keys(cb.FullTrapdoorParams(k, s), cs, fixed, sigmas, vk_repr=0x5EED)
+    proof = pv.create_proof(keys, advice, rng=pv.ChaCha12Rng(bytes(32)))
+    assert pv.verify_proof_with_trapdoor(keys, proof, s)
+    assert proof == open(GOLDEN_PROOF, "rb").read()
+
+
+@pytest.mark.gpu
+def test_device_proof_bytes_equal_the_cpu_oracle_proof_bytes():
+    """Same SRS trapdoor, circuit, witness and transcript seed: the proof produced through the CUDA library (real SRS, MSM commitments,
+    device NTTs / evaluate_h / scans) is BYTE-IDENTICAL to the one produced with every primitive on the CPU oracle (the golden file).
+    This is the north star's bit-identical-proof claim with the CPU port standing in for the Rust prover."""
+    from ezkl_b200 import _native as nat
+    from ezkl_b200 import halo2 as h2
+    nat.init(-1)
+    k, s, cs, fixed, sigmas, advice = golden_case()
+    keys = pv.Keys(h2.ParamsKZG.setup(k, s), cs, fixed, sigmas, vk_repr=0x5EED)
+    proof = pv.create_proof(keys, advice, rng=pv.ChaCha12Rng(bytes(32)))
+    assert proof == open(GOLDEN_PROOF, "rb").read()
+
+
 @pytest.mark.gpu
 def test_prove_and_verify_round_trip_with_trapdoor_srs():
     from ezkl_b200 import _native as nat
@@ -172,3 +211,19 @@ def test_prove_and_verify_round_trip_with_trapdoor_srs():
     advice_bad[tcs.OUT][3] = (advice_bad[tcs.OUT][3] + 1) % R
     proof_bad = pv.create_proof(keys, advice_bad, rng=pv.ChaCha12Rng(bytes(32)))
     assert not pv.verify_proof_with_trapdoor(keys, proof_bad, s)
+
+
+if __name__ == "__main__":          # python tests/test_prover_mirror.py --regenerate : rewrite the golden proof with the CPU backend
+    import sys
+    if "--regenerate" in sys.argv:
+        from _pytest.monkeypatch import MonkeyPatch
+        from tests import cpu_backend as cb
+        mp = MonkeyPatch()
+        cb.patch_backend(mp)
+        k, s, cs, fixed, sigmas, advice = golden_case()
+        keys = pv.Keys(cb.FullTrapdoorParams(k, s), cs, fixed, sigmas, vk_repr=0x5EED)
+        data = pv.create_proof(keys, advice, rng=pv.ChaCha12Rng(bytes(32)))
+        assert pv.verify_proof_with_trapdoor(keys, data, s)
+        open(GOLDEN_PROOF, "wb").write(data)
+        mp.undo()
+        print("wrote %s (%d bytes, sha256 %s)" % (GOLDEN_PROOF, len(data), hashlib.sha256(data).hexdigest()))
