@@ -222,3 +222,26 @@ def test_generated_field_arithmetic_is_verified_and_current(tmp_path):
     for name, mod in gen.FIELDS.items():
         for fn, ins, n_in in (("mul", gen.gen_mul(mod), 2), ("mul2", gen.gen_mul2(mod), 4), ("sqr", gen.gen_sqr(mod), 1)):
             assert gen.emit_fn("%s_%s_ptx" % (name, fn), ins, n_in) in committed, "%s_%s_ptx is stale: run fp_gen.py" % (name, fn)
+
+
+def test_keygen_host_logic_reproduces_reference_proving_key_bytes_on_the_cpu_backend(monkeypatch):
+    """create_keys' derived vectors (src/pfsys/mod.rs:376-400) through the SAME host code the GPU test drives (ProvingKey.keygen_pk_polys,
+    EvaluationDomain.keygen_l_polys: which rows l_last / the blinding rows sit on, how l_active_row is formed, which columns are
+    transformed how), with the transforms redirected to the CPU oracle: byte for byte the reference pk.key's polys, extended cosets, l0,
+    l_last and l_active_row (tests/golden/pk_k6_subset.npz)."""
+    from ezkl_b200 import halo2 as h2
+    from tests import cpu_backend as cb
+    cb.patch_backend(monkeypatch)
+    pk = H.load_pk_fixture()
+    key = h2.ProvingKey()
+    key.k = 6
+    cols = (0, 1, 5, 37)
+    key.fixed_values = [pk["fixed_values_%d" % c] for c in cols]
+    key.permutations = [pk["perm_values_0"]]
+    out = key.keygen_pk_polys(9, 5)
+    for i, c in enumerate(cols):
+        assert np.array_equal(out["fixed_polys"][i], pk["fixed_polys_%d" % c])
+        assert np.array_equal(out["fixed_cosets"][i], pk["fixed_cosets_%d" % c])
+    assert np.array_equal(out["permutation_polys"][0], pk["perm_polys_0"])
+    assert np.array_equal(out["permutation_cosets"][0], pk["perm_cosets_0"])
+    assert np.array_equal(out["l0"], pk["l0"]) and np.array_equal(out["l_last"], pk["l_last"]) and np.array_equal(out["l_active_row"], pk["l_active_row"])
