@@ -245,3 +245,21 @@ def test_keygen_host_logic_reproduces_reference_proving_key_bytes_on_the_cpu_bac
     assert np.array_equal(out["permutation_polys"][0], pk["perm_polys_0"])
     assert np.array_equal(out["permutation_cosets"][0], pk["perm_cosets_0"])
     assert np.array_equal(out["l0"], pk["l0"]) and np.array_equal(out["l_last"], pk["l_last"]) and np.array_equal(out["l_active_row"], pk["l_active_row"])
+
+
+def test_bench_trace_shape_matches_the_reference_fixture_proof():
+    """bench.py's default op trace is shaped like the reference's own fixture proof (tests/assets/proof.json):
+    114 commitments + 2 SHPLONK points, 231 evaluations; config dicts of the two bench arms are the same object shape."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    tr = bench.TRACES["conv2d_mnist"]
+    ops = bench.trace_ops(tr)
+    msm_cols = [c for kind, c in ops if kind.startswith("msm")]
+    assert sum(msm_cols) == 114 + 2 and msm_cols[-1] == 2
+    assert dict(ops)["eval"] == 231
+    assert bench.n_coset_columns(tr) == tr["advice"] + tr["instance"] + tr["perm_z"] + 2 * tr["lookups"] == 107
+    pairs, ntt_elts = bench.count_units(ops, 1 << 17, tr)
+    assert pairs == 116 << 17 and ntt_elts == (107 << 17) + (108 << 20)
+    cfg = bench.make_config(17, "conv2d_mnist")
+    assert cfg["k"] == 17 and cfg["msm_pairs_per_step"] == pairs and "workload" in cfg
