@@ -353,10 +353,10 @@ def _affine_wire(pt) -> np.ndarray:
     return np.concatenate([F.fq_to_limbs(pt[0]), F.fq_to_limbs(pt[1])])
 
 
-def verify_proof_with_trapdoor(keys: Keys, proof: bytes, s: int, instances=()) -> bool:
-    """VerifierSHPLONK + the PLONK identity check, restated (UPSTREAM plonk/verifier.rs, shplonk/verifier.rs).  The final pairing
-    e(L, [1]_2) == e(h2, [s]_2) becomes the group equation L - s * h2 == identity, computed as ONE MSM on the device over the proof's
-    and the key's commitments."""
+def _verifier_accumulate(keys: Keys, proof: bytes, instances=()):
+    """VerifierSHPLONK + the PLONK identity check, restated (UPSTREAM plonk/verifier.rs, shplonk/verifier.rs), up to the final pairing:
+    returns (acc, h2_pt, u) with acc = {point: scalar} ("G" = the generator) such that the verifier's left input is
+    L = sum acc[pt] * pt + u * h2 and its check is e(L, [1]_2) == e(h2, [s]_2); None when the proof is malformed."""
     cs, params, dom = keys.cs, keys.params, keys.domain
     n, bf = params.n, cs.blinding_factors
     na = cs.num_advice
@@ -383,7 +383,7 @@ def verify_proof_with_trapdoor(keys: Keys, proof: bytes, s: int, instances=()) -
         z_e = [[tr.read_scalar() for _ in range(3 if i + 1 < cs.num_z else 2)] for i in range(cs.num_z)]
         lk_e = [[tr.read_scalar() for _ in range(3)] for _ in cs.lookups]
     except ValueError:
-        return False
+        return None
     w = F.fr_from_limbs(dom.omega)
     rot_pt = lambda rot: x * pow(w, rot, R) % R
     last_rot = -(bf + 1)
@@ -411,7 +411,7 @@ def verify_proof_with_trapdoor(keys: Keys, proof: bytes, s: int, instances=()) -
     try:
         numerator = expr_eval(cs.numerator(beta, gamma, y), lambda c, rot: table[(c, rot)])
     except KeyError:
-        return False
+        return None
     expected_h = numerator * pow(xn - 1, -1, R) % R
     # openings as (list of (scalar, point)) commitments, point, eval — same order as the prover's queries
     qs = [([(1, adv_c[c])], rot_pt(rot), v) for (c, rot), v in zip(cs.advice_queries, adv_e)]
@@ -432,9 +432,9 @@ def verify_proof_with_trapdoor(keys: Keys, proof: bytes, s: int, instances=()) -
         u = tr.squeeze_challenge()
         h2_pt = tr.read_ec_point()
     except ValueError:
-        return False
+        return None
     if tr.pos != len(proof):
-        return False
+        return None
     # rotation sets keyed by the commitment's identity (same grouping rule as the prover: first appearance order)
     by_commit, order = {}, []
     for comm, pt, val in qs:
@@ -477,19 +477,46 @@ def verify_proof_with_trapdoor(keys: Keys, proof: bytes, s: int, instances=()) -
                 add(cj * sc, pt)
             add(-cj * r_u, "G")
     add(-zt * z0_inv, h1)
-    add(u - s, h2_pt)                                                  # + u * h2 - s * h2
+    return acc, h2_pt, u
+
+
+def _msm_points(acc):
+    """sum acc[pt] * pt as ONE MSM over the proof's and the key's commitments (normalised Jacobian wire; z = 0 for the identity)."""
     pts, scs = [], []
     for pt, sc in acc.items():
-        if pt is None or sc == 0:
+        if pt is None or sc % R == 0:
             continue
         pts.append(_affine_wire((1, 2) if pt == "G" else pt))
-        scs.append(F.fr_to_limbs(sc))
+        scs.append(F.fr_to_limbs(sc % R))
     if not pts:
-        return True
+        return np.array([0] * 4 + list(F.fq_to_limbs(1)) + [0] * 4, np.uint64)
     bases = h2.Bases(np.stack(pts))
     res = h2.best_multiexp(np.stack(scs), bases)
     bases.release()
-    return not res[8:].any()                                           # normalised identity has z = 0
+    return res
+
+
+def verify_proof_with_trapdoor(keys: Keys, proof: bytes, s: int, instances=()) -> bool:
+    """The restated verifier with the final pairing e(L, [1]_2) == e(h2, [s]_2) replaced by the group equation L - s * h2 == identity
+    (the trapdoor s of a test SRS is known), computed as ONE MSM."""
+    r = _verifier_accumulate(keys, proof, instances)
+    if r is None:
+        return False
+    acc, h2_pt, u = r
+    acc[h2_pt] = (acc.get(h2_pt, 0) + u - s) % R                      # + u * h2 - s * h2
+    return not _msm_points(acc)[8:].any()                              # normalised identity has z = 0
+
+
+def verify_proof_with_pairing(keys: Keys, proof: bytes, pairing_check, instances=()) -> bool:
+    """The restated verifier with the REAL final check: pairing_check(L, h2) must decide e(L, [1]_2) == e(h2, [s]_2) for the SRS the
+    keys were made with (L, h2 affine (x, y) python ints or None for the identity).  The pairing itself is not on the prover's path and
+    is supplied by the caller (tests/pairing_bn254.py runs it on the reference's own SRS fixture)."""
+    r = _verifier_accumulate(keys, proof, instances)
+    if r is None:
+        return False
+    acc, h2_pt, u = r
+    acc[h2_pt] = (acc.get(h2_pt, 0) + u) % R
+    return bool(pairing_check(_jac_to_xy(_msm_points(acc)), h2_pt))
 
 
 def _jac_to_xy(j):
